@@ -1,0 +1,218 @@
+"""Synthetic nuScenes-shaped workloads for the BEV-encoder hot path (SURVEY.md §8 shape table, §8d).
+
+There is no dataset and no checkpoint on the box: every test, golden vector and bench line uses
+tensors of the shapes the reference's shipped configs produce, filled from a seeded generator,
+and a synthetic six-camera rig whose projection matrices play the role of
+``img_metas[i]['lidar2img']`` (reference: projects/mmdet3d_plugin/datasets/nuscenes_dataset.py:105-167).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+
+
+@dataclass(frozen=True)
+class Workload:
+    """One row of SURVEY.md §8's shape table."""
+    name: str
+    bev_h: int
+    bev_w: int
+    num_layers: int
+    levels: Tuple[Tuple[int, int], ...]          # (H_l, W_l) per FPN level
+    img_hw: Tuple[int, int]                      # padded image (H, W) == img_metas img_shape
+    scale: float                                 # image scale applied to the 900x1600 rig
+    num_cams: int = 6
+    embed_dims: int = 256
+    num_heads: int = 8
+    ffn_dims: int = 512
+    pillar_points: int = 4                       # num_points_in_pillar (D)
+    sca_points: int = 8
+    tsa_points: int = 4
+    config_file: Optional[str] = None            # reference config this mirrors, if shipped
+
+    @property
+    def num_query(self) -> int:
+        return self.bev_h * self.bev_w
+
+    @property
+    def num_value(self) -> int:
+        return sum(h * w for h, w in self.levels)
+
+    @property
+    def level_start(self) -> List[int]:
+        out, s = [], 0
+        for h, w in self.levels:
+            out.append(s)
+            s += h * w
+        return out
+
+
+WORKLOADS = {
+    # projects/configs/bevformer/bevformer_tiny.py:45-48,59,70,90,184-185
+    "tiny": Workload("tiny", 50, 50, 3, ((15, 25),), (480, 800), 0.5,
+                     config_file="bevformer/bevformer_tiny.py"),
+    # projects/configs/bevformer/bevformer_small.py:41-44,54,68,88,182-183 (single-level C5)
+    "small": Workload("small", 150, 150, 3, ((23, 40),), (736, 1280), 0.8,
+                      config_file="bevformer/bevformer_small.py"),
+    # BASELINE.json configs[2]: small with a synthetic 4-level pyramid
+    "small4": Workload("small4", 150, 150, 3, ((92, 160), (46, 80), (23, 40), (12, 20)),
+                       (736, 1280), 0.8),
+    # projects/configs/bevformer/bevformer_base.py:34-37,47,60,80
+    "base": Workload("base", 200, 200, 6, ((116, 200), (58, 100), (29, 50), (15, 25)),
+                     (928, 1600), 1.0, config_file="bevformer/bevformer_base.py"),
+    # a toy used by fast CPU tests (not a reference config)
+    "toy": Workload("toy", 12, 10, 2, ((8, 14), (4, 7)), (64, 112), 0.07),
+}
+
+
+def encoder_cfg(w: Workload) -> dict:
+    """The encoder dict the reference configs spell out (bevformer_base.py:78-105), for workloads
+    that have no shipped config file (small4, toy). Shipped configs are read from their files."""
+    return dict(
+        type="BEVFormerEncoder", num_layers=w.num_layers, pc_range=list(PC_RANGE),
+        num_points_in_pillar=w.pillar_points, return_intermediate=False,
+        transformerlayers=dict(
+            type="BEVFormerLayer",
+            attn_cfgs=[
+                dict(type="TemporalSelfAttention", embed_dims=w.embed_dims, num_levels=1),
+                dict(type="SpatialCrossAttention", pc_range=list(PC_RANGE),
+                     deformable_attention=dict(type="MSDeformableAttention3D",
+                                               embed_dims=w.embed_dims,
+                                               num_points=w.sca_points,
+                                               num_levels=len(w.levels)),
+                     embed_dims=w.embed_dims),
+            ],
+            feedforward_channels=w.ffn_dims, ffn_dropout=0.1,
+            operation_order=("self_attn", "norm", "cross_attn", "norm", "ffn", "norm")))
+
+
+# ------------------------------------------------------------------------------------------------
+# camera rig: lidar frame x-right / y-forward / z-up
+# ------------------------------------------------------------------------------------------------
+_YAWS_DEG = (0.0, -55.0, 55.0, 180.0, 110.0, -110.0)
+_FOCALS = (1266.4, 1260.8, 1272.6, 809.2, 1256.7, 1259.5)
+_PRINCIPAL = (816.0, 491.5)
+_CAM_AHEAD, _CAM_BELOW = 1.0, 0.3   # each camera sits 1 m along its own optical axis, 0.3 m below the lidar
+
+
+def make_lidar2img(scale: float = 1.0, num_cams: int = 6) -> np.ndarray:
+    """(num_cams, 4, 4) float64 projection matrices: pixel = K(scale) @ [R | -R c] @ (x, y, z, 1)."""
+    mats = []
+    for i in range(num_cams):
+        yaw = math.radians(_YAWS_DEG[i % 6])
+        fwd = np.array([-math.sin(yaw), math.cos(yaw), 0.0])
+        right = np.array([math.cos(yaw), math.sin(yaw), 0.0])
+        down = np.array([0.0, 0.0, -1.0])
+        rot = np.stack([right, down, fwd])                       # lidar -> camera axes
+        ext = np.eye(4)
+        ext[:3, :3] = rot
+        pos = fwd * _CAM_AHEAD + np.array([0.0, 0.0, -_CAM_BELOW])
+        ext[:3, 3] = -rot @ pos
+        f = _FOCALS[i % 6] * scale
+        k = np.eye(4)
+        k[0, 0] = k[1, 1] = f
+        k[0, 2] = _PRINCIPAL[0] * scale
+        k[1, 2] = _PRINCIPAL[1] * scale
+        mats.append(k @ ext)
+    return np.stack(mats)
+
+
+def make_img_metas(w: Workload, bs: int = 1):
+    l2i = make_lidar2img(w.scale, w.num_cams)
+    h, wd = w.img_hw
+    return [dict(lidar2img=[l2i[i].copy() for i in range(w.num_cams)],
+                 img_shape=[(h, wd, 3)] * w.num_cams) for _ in range(bs)]
+
+
+@dataclass
+class EncoderInputs:
+    bev_query: torch.Tensor          # (Nq, bs, C)
+    feat: torch.Tensor               # (num_cams, S, bs, C)   key == value
+    bev_pos: torch.Tensor            # (Nq, bs, C)
+    prev_bev: Optional[torch.Tensor]  # (Nq, bs, C) or None
+    shift: torch.Tensor              # (bs, 2)
+    spatial_shapes: torch.Tensor     # (L, 2) int64 (h, w)
+    level_start_index: torch.Tensor  # (L,) int64
+    img_metas: list = field(default_factory=list)
+    bev_h: int = 0
+    bev_w: int = 0
+
+    def kwargs(self):
+        return dict(bev_h=self.bev_h, bev_w=self.bev_w, bev_pos=self.bev_pos,
+                    spatial_shapes=self.spatial_shapes, level_start_index=self.level_start_index,
+                    prev_bev=self.prev_bev, shift=self.shift, img_metas=self.img_metas)
+
+
+def make_encoder_inputs(w: Workload, bs: int = 1, seed: int = 0, with_prev: bool = True,
+                        dtype=torch.float32, device="cpu") -> EncoderInputs:
+    """Seeded N(0,1) tensors of the encoder's input contract (modules/transformer.py:186-198)."""
+    g = torch.Generator().manual_seed(seed)
+    c = w.embed_dims
+
+    def rn(*shape):
+        return torch.randn(*shape, generator=g, dtype=torch.float32)
+
+    bev_query = rn(w.num_query, 1, c).repeat(1, bs, 1)           # one embedding table, per sample
+    feat = rn(w.num_cams, w.num_value, bs, c)
+    feat = feat + rn(w.num_cams, 1, 1, c)                        # cams_embeds
+    lvl = rn(len(w.levels), c)
+    for i, (s0, (h, ww)) in enumerate(zip(w.level_start, w.levels)):
+        feat[:, s0:s0 + h * ww] += lvl[i]                        # level_embeds
+    bev_pos = torch.rand(w.num_query, 1, c, generator=g).repeat(1, bs, 1)
+    prev_bev = rn(w.num_query, bs, c) if with_prev else None
+    shift = torch.tensor([[0.01, -0.02]], dtype=torch.float32).repeat(bs, 1)
+    ss = torch.tensor(w.levels, dtype=torch.int64)
+    lsi = torch.tensor(w.level_start, dtype=torch.int64)
+
+    def cv(t):
+        return None if t is None else t.to(device=device, dtype=dtype).contiguous()
+
+    return EncoderInputs(cv(bev_query), cv(feat), cv(bev_pos), cv(prev_bev),
+                         shift.to(device=device, dtype=dtype), ss.to(device), lsi.to(device),
+                         make_img_metas(w, bs), w.bev_h, w.bev_w)
+
+
+def randomize_trained_like(module: torch.nn.Module, seed: int = 1) -> None:
+    """Second weight set of SURVEY.md §8d: the reference initialisers leave sampling offsets and
+    attention logits query-independent (zero weights); perturb them so both depend on the query."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("sampling_offsets.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif name.endswith("attention_weights.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            elif name.endswith("attention_weights.bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            elif ".norms." in name and name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif ".norms." in name and name.endswith("bias"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+            elif name.endswith(".bias") and "sampling_offsets" not in name:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+
+
+# ------------------------------------------------------------------------------------------------
+# op-level micro workloads (loc ~ U(-0.1, 1.1), attn = softmax(N(0,1)))
+# ------------------------------------------------------------------------------------------------
+def make_msda_inputs(bs, levels, num_query, num_heads=8, head_dim=32, num_points=4, seed=0,
+                     dtype=torch.float32, device="cpu", value_scale=1.0, loc_range=(-0.1, 1.1)):
+    g = torch.Generator().manual_seed(seed)
+    s = sum(h * w for h, w in levels)
+    nl = len(levels)
+    value = torch.randn(bs, s, num_heads, head_dim, generator=g) * value_scale
+    lo, hi = loc_range
+    loc = torch.rand(bs, num_query, num_heads, nl, num_points, 2, generator=g) * (hi - lo) + lo
+    attn = torch.randn(bs, num_query, num_heads, nl * num_points, generator=g).softmax(-1)
+    attn = attn.view(bs, num_query, num_heads, nl, num_points)
+    ss = torch.tensor(levels, dtype=torch.int64)
+    lsi = torch.cat([ss.new_zeros(1), (ss[:, 0] * ss[:, 1]).cumsum(0)[:-1]])
+    return (value.to(device=device, dtype=dtype).contiguous(), ss.to(device), lsi.to(device),
+            loc.to(device=device, dtype=dtype).contiguous(),
+            attn.to(device=device, dtype=dtype).contiguous())

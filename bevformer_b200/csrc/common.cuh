@@ -1,0 +1,126 @@
+// Shared device/host helpers for the bevformer_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "../../include/bevformer_b200.h"
+
+namespace bevf {
+
+// ---- host side: error string + launch accounting ----------------------------------------------
+std::string &last_error();
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(const char *fmt, const char *a = "", long long x = 0, long long y = 0) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), fmt, a, x, y);
+    last_error() = buf;
+    return 1;
+}
+
+inline int check_launch(const char *what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: launch failed: %s", what, cudaGetErrorString(e));
+        last_error() = buf;
+        return 2;
+    }
+    return 0;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device side ------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    // cvt.rn.bf16x2.f32 d, a, b  puts a in the upper half, b in the lower half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// A "row" is the 32 contiguous channels of one (pixel, head).  kVec channels per lane, 16 B each.
+template <typename T> struct Row;
+template <> struct Row<float> {
+    static constexpr int kVec = 4;
+    __device__ static __forceinline__ void load(const float *p, float (&v)[4]) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ static __forceinline__ void store(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __device__ static __forceinline__ float load1(const float *p) { return __ldg(p); }
+    __device__ static __forceinline__ void store1(float *p, float v) { *p = v; }
+};
+template <> struct Row<bf16> {
+    static constexpr int kVec = 8;
+    __device__ static __forceinline__ void load(const bf16 *p, float (&v)[8]) {
+        uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+        v[4] = bf16_lo(t.z); v[5] = bf16_hi(t.z); v[6] = bf16_lo(t.w); v[7] = bf16_hi(t.w);
+    }
+    __device__ static __forceinline__ void store(bf16 *p, const float (&v)[8]) {
+        uint4 t;
+        t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+        t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(p) = t;
+    }
+    __device__ static __forceinline__ float load1(const bf16 *p) {
+        return __bfloat162float(*p);
+    }
+    __device__ static __forceinline__ void store1(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// N consecutive channels (N = 4 or 8) <-> fp32 registers, for either storage type.
+template <typename T, int N> __device__ __forceinline__ void load_vec(const T *p, float (&v)[N]);
+template <> __device__ __forceinline__ void load_vec<float, 4>(const float *p, float (&v)[4]) {
+    Row<float>::load(p, v);
+}
+template <> __device__ __forceinline__ void load_vec<float, 8>(const float *p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load_vec<bf16, 8>(const bf16 *p, float (&v)[8]) {
+    Row<bf16>::load(p, v);
+}
+template <> __device__ __forceinline__ void load_vec<bf16, 4>(const bf16 *p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+}
+template <typename T, int N> __device__ __forceinline__ void store_vec(T *p, const float (&v)[N]);
+template <> __device__ __forceinline__ void store_vec<float, 4>(float *p, const float (&v)[4]) {
+    Row<float>::store(p, v);
+}
+template <> __device__ __forceinline__ void store_vec<float, 8>(float *p, const float (&v)[8]) {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store_vec<bf16, 8>(bf16 *p, const float (&v)[8]) {
+    Row<bf16>::store(p, v);
+}
+template <> __device__ __forceinline__ void store_vec<bf16, 4>(bf16 *p, const float (&v)[4]) {
+    *reinterpret_cast<uint2 *>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
+// 16-byte fp32 vector reduction into global memory (SASS: REDG.E.ADD.F32x4).
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+}  // namespace bevf

@@ -216,3 +216,66 @@ def make_msda_inputs(bs, levels, num_query, num_heads=8, head_dim=32, num_points
     return (value.to(device=device, dtype=dtype).contiguous(), ss.to(device), lsi.to(device),
             loc.to(device=device, dtype=dtype).contiguous(),
             attn.to(device=device, dtype=dtype).contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic encoder weights, independent of any module's construction order
+# ------------------------------------------------------------------------------------------------
+def _ring_bias(num_heads: int, groups: int, num_points: int) -> torch.Tensor:
+    """The reference's sampling-offset bias: head m points along direction 2*pi*m/M (scaled to the
+    unit square), point i at radius i+1 (spatial_cross_attention.py:255-267,
+    temporal_self_attention.py:109-122). ``groups`` = num_levels (x num_bev_queue for TSA)."""
+    th = torch.arange(num_heads, dtype=torch.float32) * (2.0 * math.pi / num_heads)
+    d = torch.stack([th.cos(), th.sin()], -1)
+    d = (d / d.abs().max(-1, keepdim=True)[0]).view(num_heads, 1, 1, 2).repeat(1, groups, num_points, 1)
+    for i in range(num_points):
+        d[:, :, i, :] *= i + 1
+    return d.reshape(-1)
+
+
+def make_state_dict(w: Workload, seed: int = 0, trained_like: bool = True, dtype=torch.float32):
+    """Encoder ``state_dict`` with the reference's key names and shapes.
+    ``trained_like=False`` reproduces the reference initialisers (zero offset/attention weights);
+    ``True`` perturbs them so that offsets and attention logits depend on the query."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    c, m, f = w.embed_dims, w.num_heads, w.ffn_dims
+    nl = len(w.levels)
+
+    def xavier(o, i):
+        a = math.sqrt(6.0 / (i + o))
+        return (torch.rand(o, i, generator=g) * 2 - 1) * a
+
+    def rn(*s, std=1.0):
+        return torch.randn(*s, generator=g) * std
+
+    sd = {}
+    for li in range(w.num_layers):
+        p = f"layers.{li}."
+        t, s = p + "attentions.0.", p + "attentions.1."
+        n_off_t, n_att_t = 2 * m * 1 * w.tsa_points * 2, 2 * m * 1 * w.tsa_points
+        sd[t + "sampling_offsets.weight"] = rn(n_off_t, 2 * c, std=0.02) if trained_like else torch.zeros(n_off_t, 2 * c)
+        sd[t + "sampling_offsets.bias"] = _ring_bias(m, 1 * 2, w.tsa_points)
+        sd[t + "attention_weights.weight"] = rn(n_att_t, 2 * c, std=0.1) if trained_like else torch.zeros(n_att_t, 2 * c)
+        sd[t + "attention_weights.bias"] = rn(n_att_t, std=0.1) if trained_like else torch.zeros(n_att_t)
+        sd[t + "value_proj.weight"] = xavier(c, c)
+        sd[t + "value_proj.bias"] = rn(c, std=0.02) if trained_like else torch.zeros(c)
+        sd[t + "output_proj.weight"] = xavier(c, c)
+        sd[t + "output_proj.bias"] = rn(c, std=0.02) if trained_like else torch.zeros(c)
+        d = s + "deformable_attention."
+        n_off_s, n_att_s = m * nl * w.sca_points * 2, m * nl * w.sca_points
+        sd[d + "sampling_offsets.weight"] = rn(n_off_s, c, std=0.02) if trained_like else torch.zeros(n_off_s, c)
+        sd[d + "sampling_offsets.bias"] = _ring_bias(m, nl, w.sca_points)
+        sd[d + "attention_weights.weight"] = rn(n_att_s, c, std=0.1) if trained_like else torch.zeros(n_att_s, c)
+        sd[d + "attention_weights.bias"] = rn(n_att_s, std=0.1) if trained_like else torch.zeros(n_att_s)
+        sd[d + "value_proj.weight"] = xavier(c, c)
+        sd[d + "value_proj.bias"] = rn(c, std=0.02) if trained_like else torch.zeros(c)
+        sd[s + "output_proj.weight"] = xavier(c, c)
+        sd[s + "output_proj.bias"] = rn(c, std=0.02) if trained_like else torch.zeros(c)
+        sd[p + "ffns.0.layers.0.0.weight"] = xavier(f, c)
+        sd[p + "ffns.0.layers.0.0.bias"] = rn(f, std=0.02)
+        sd[p + "ffns.0.layers.1.weight"] = xavier(c, f)
+        sd[p + "ffns.0.layers.1.bias"] = rn(c, std=0.02)
+        for k in range(3):
+            sd[p + f"norms.{k}.weight"] = 1.0 + (rn(c, std=0.1) if trained_like else torch.zeros(c))
+            sd[p + f"norms.{k}.bias"] = rn(c, std=0.1) if trained_like else torch.zeros(c)
+    return {k: v.to(dtype) for k, v in sd.items()}

@@ -73,12 +73,14 @@ def point_sampling(ref_3d: Tensor, pc_range: Sequence[float], img_metas) -> tupl
     Returns reference_points_cam (cam, B, Nq, D, 2) and bev_mask (cam, B, Nq, D) bool."""
     l2i = torch.as_tensor(np.asarray([m["lidar2img"] for m in img_metas]),
                           dtype=torch.float32)                          # (B, cam, 4, 4)
-    pts = ref_3d.to(torch.float32).clone()
-    lo = torch.tensor(pc_range[:3], dtype=torch.float32)
-    hi = torch.tensor(pc_range[3:], dtype=torch.float32)
-    pts = pts * (hi - lo) + lo                                          # :102-107
-    pts = torch.cat([pts, torch.ones_like(pts[..., :1])], -1)           # (B, D, Nq, 4)
-    cam = torch.einsum("bcij,bdqj->cbqdi", l2i, pts)                    # :116-123
+    ext = [pc_range[3] - pc_range[0], pc_range[4] - pc_range[1], pc_range[5] - pc_range[2]]
+    pts = torch.stack([ref_3d[..., i] * ext[i] + pc_range[i] for i in range(3)], -1)   # :102-107,
+    pts = torch.cat([pts, torch.ones_like(pts[..., :1])], -1)           # in the caller's dtype
+    pts = pts.to(torch.float32)                                         # (B, D, Nq, 4)  :122-123
+    b, d, nq = pts.shape[:3]
+    cam = torch.matmul(l2i.view(1, b, -1, 1, 4, 4),                     # :116-123 (broadcast
+                       pts.permute(1, 0, 2, 3).reshape(d, b, 1, nq, 4, 1))   # instead of repeat)
+    cam = cam.squeeze(-1).permute(2, 1, 3, 0, 4)                        # (cam, B, Nq, D, 4)
     eps = 1e-5
     depth = cam[..., 2:3]
     mask = depth > eps                                                  # :126

@@ -1,0 +1,151 @@
+"""GPU parity tests of the sampler THROUGH THE C ABI (ops.py -> ctypes -> libbevformer_b200.so)
+against (a) the committed golden vectors made from the reference's own modules and (b) Oracle-S
+run on the same seeded inputs.  Bars: 1e-3 for fp32 storage, 1e-2 for bf16 storage
+(BASELINE.json north_star), read as max|err| / max(1, max|ref|)."""
+import numpy as np
+import pytest
+import torch
+
+from bevformer_b200 import ops, synthetic as syn
+from oracle import msda_oracle
+from tests.util import fixed_projection, golden, max_err, msda_case_inputs, rel_err, stats, stats_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float32: 1e-3, torch.bfloat16: 1e-2}
+
+
+def _run(v, ss, lsi, loc, attn, gout, dtype):
+    vd = v.to(DEV, dtype).contiguous()
+    out = ops.msda_forward(vd, ss.to(DEV), lsi.to(DEV), loc.to(DEV).float().contiguous(),
+                           attn.to(DEV).float().contiguous())
+    gv, gl, ga = ops.msda_backward(vd, ss.to(DEV), lsi.to(DEV), loc.to(DEV).float().contiguous(),
+                                   attn.to(DEV).float().contiguous(),
+                                   gout.to(DEV, dtype).contiguous())
+    torch.cuda.synchronize()
+    return out.float().cpu(), gv.cpu(), gl.cpu(), ga.cpu()
+
+
+@pytest.mark.parametrize("case", ["kat", "kat_oob", "config0", "pyramid"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_against_golden(case, dtype):
+    g = golden("msda_" + case)
+    v, ss, lsi, loc, attn = msda_case_inputs(g, torch.float32)
+    gout = fixed_projection((v.shape[0], loc.shape[1], v.shape[2] * v.shape[3]))
+    out, gv, gl, ga = _run(v, ss, lsi, loc, attn, gout, dtype)
+    rq, rs = g["rows_q"], g["rows_s"]
+    tol = TOL[dtype]
+    assert rel_err(out[:, rq], g["out_rows"]) < tol
+    assert rel_err(gv[:, rs], g["grad_value_rows"]) < tol
+    assert rel_err(ga[:, rq], g["grad_attn_rows"]) < tol
+    assert rel_err(gl[:, rq], g["grad_loc_rows"]) < tol * 4   # carries the W_l / H_l factors
+    assert stats_close(stats(out), g["out_stats"], 10 * tol)
+    assert stats_close(stats(gv), g["grad_value_stats"], 10 * tol)
+
+
+@pytest.mark.parametrize("dim", [4, 30, 32, 64, 71, 1025])   # mmcv's gradcheck channel list
+def test_head_dims_against_oracle(dim):
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(2, [(6, 4), (3, 2)], 9, 2, dim, 2, seed=dim,
+                                                 loc_range=(-0.3, 1.3))
+    gout = fixed_projection((2, 9, 2 * dim))
+    out, gv, gl, ga = _run(v, ss, lsi, loc, attn, gout, torch.float32)
+    ref = msda_oracle.msda_forward(v, ss, lsi, loc, attn)
+    rgv, rgl, rga = msda_oracle.msda_backward(v, ss, lsi, loc, attn, gout)
+    assert max_err(out, ref) < 1e-4
+    assert max_err(gv, rgv) < 1e-4 and max_err(gl, rgl) < 1e-3 and max_err(ga, rga) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [
+    dict(bs=1, levels=[(1, 1)], nq=1, heads=1, pts=1),            # smallest possible
+    dict(bs=3, levels=[(7, 5)], nq=33, heads=3, pts=5),           # ragged: heads not a power of two
+    dict(bs=2, levels=[(9, 11), (5, 6), (3, 3), (2, 2), (1, 1)], nq=65, heads=8, pts=3),
+    dict(bs=6, levels=[(15, 25)], nq=592, heads=8, pts=8),        # tiny's SCA shape (max_len 592)
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_shapes_against_oracle(shape, dtype):
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(shape["bs"], shape["levels"], shape["nq"],
+                                                 shape["heads"], 32, shape["pts"], seed=2,
+                                                 loc_range=(-0.2, 1.2))
+    if dtype == torch.bfloat16:   # compare against the oracle on the SAME (bf16-rounded) inputs
+        v = v.to(dtype).float()
+    gout = fixed_projection((shape["bs"], shape["nq"], shape["heads"] * 32))
+    if dtype == torch.bfloat16:
+        gout = gout.to(dtype).float()
+    out, gv, gl, ga = _run(v, ss, lsi, loc, attn, gout, dtype)
+    ref = msda_oracle.msda_forward(v, ss, lsi, loc, attn)
+    rgv, rgl, rga = msda_oracle.msda_backward(v, ss, lsi, loc, attn, gout)
+    otol = 1e-4 if dtype == torch.float32 else 1e-2       # bf16 output rounding
+    assert rel_err(out, ref) < otol
+    assert rel_err(gv, rgv) < 1e-4 and rel_err(ga, rga) < 1e-4 and rel_err(gl, rgl) < 1e-3
+
+
+def test_empty_and_extreme_locations():
+    ss = torch.tensor([[4, 5]], device=DEV); lsi = torch.tensor([0], device=DEV)
+    value = torch.randn(1, 20, 1, 32, device=DEV)
+    out = ops.msda_forward(value, ss, lsi, torch.zeros(1, 0, 1, 1, 1, 2, device=DEV),
+                           torch.zeros(1, 0, 1, 1, 1, device=DEV))
+    assert out.shape == (1, 0, 32)
+    far = torch.tensor([[-0.5 / 5 - 1e-6, 0.5], [1.0 + 0.5 / 5, 0.5], [0.5, -0.125 - 1e-6],
+                        [0.5, 1.125], [1e9, 0.5], [0.5, -1e9], [float("nan"), 0.5],
+                        [float("inf"), 0.5]], device=DEV).view(1, 8, 1, 1, 1, 2)
+    w = torch.ones(1, 8, 1, 1, 1, device=DEV)
+    out = ops.msda_forward(value, ss, lsi, far.contiguous(), w)
+    assert out.abs().max().item() == 0.0
+    gv, gl, ga = ops.msda_backward(value, ss, lsi, far.contiguous(), w, torch.ones_like(out))
+    assert gv.abs().max().item() == 0.0 and gl.abs().max().item() == 0.0 and ga.abs().max().item() == 0.0
+
+
+def test_pixel_centres_reproduce_value_and_permutation():
+    ss = torch.tensor([[6, 7]], device=DEV); lsi = torch.tensor([0], device=DEV)
+    value = torch.randn(2, 42, 8, 32, device=DEV)
+    ys, xs = torch.meshgrid(torch.arange(6.0), torch.arange(7.0), indexing="ij")
+    loc = torch.stack([(xs + 0.5) / 7, (ys + 0.5) / 6], -1).reshape(1, 42, 1, 1, 1, 2)
+    loc = loc.expand(2, 42, 8, 1, 1, 2).contiguous().to(DEV)
+    w = torch.ones(2, 42, 8, 1, 1, device=DEV)
+    out = ops.msda_forward(value, ss, lsi, loc, w)
+    assert max_err(out, value.view(2, 42, 256)) < 1e-5
+    perm = torch.randperm(42, device=DEV)
+    out_p = ops.msda_forward(value, ss, lsi, loc[:, perm].contiguous(), w)
+    assert torch.equal(out_p, out[:, perm])
+
+
+def test_autograd_function_contract():
+    """Same apply() signature and 6-tuple of grads as the reference class
+    (multi_scale_deformable_attn_function.py:94-95,162-163)."""
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(2, [(5, 4), (3, 2)], 6, 4, 32, 2, seed=1, device=DEV)
+    v.requires_grad_(); loc.requires_grad_(); attn.requires_grad_()
+    out = ops.MultiScaleDeformableAttnFunction_fp32.apply(v, ss, lsi, loc, attn, 64)
+    assert out.shape == (2, 6, 128)
+    out.sum().backward()
+    assert v.grad.shape == v.shape and loc.grad.shape == loc.shape and attn.grad.shape == attn.shape
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ops.MultiScaleDeformableAttnFunction_fp32.apply(v.detach().transpose(1, 2), ss, lsi,
+                                                        loc.detach(), attn.detach(), 64)
+    with pytest.raises(RuntimeError, match="im2col_step"):
+        ops.MultiScaleDeformableAttnFunction_fp32.apply(v.detach()[:1].repeat(3, 1, 1, 1), ss, lsi,
+                                                        loc.detach()[:1].repeat(3, 1, 1, 1, 1, 1),
+                                                        attn.detach()[:1].repeat(3, 1, 1, 1, 1), 2)
+
+
+@pytest.mark.parametrize("which", ["tsa", "sca"])
+def test_base_shapes_properties(which):
+    """Full BASELINE sizes: linearity in value / attn and agreement with Oracle-S on a row sample."""
+    w = syn.WORKLOADS["base"]
+    if which == "tsa":
+        bs, levels, nq, pts = 2, [(200, 200)], 40000, 4
+    else:
+        bs, levels, nq, pts = 6, list(w.levels), 9507, 8
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(bs, levels, nq, 8, 32, pts, seed=0)
+    vd, ld, ad = v.to(DEV), loc.to(DEV), attn.to(DEV)
+    out = ops.msda_forward(vd, ss.to(DEV), lsi.to(DEV), ld, ad)
+    out2 = ops.msda_forward(2 * vd, ss.to(DEV), lsi.to(DEV), ld, 0.5 * ad)
+    assert max_err(out2, out) < 1e-4
+    rows = np.sort(np.random.default_rng(0).choice(nq, 64, replace=False))
+    ref = msda_oracle.msda_forward(v, ss, lsi, loc[:, rows].contiguous(), attn[:, rows].contiguous())
+    assert max_err(out[:, rows].cpu(), ref) < 1e-4
+    # backward: grad_value total mass equals sum over samples of in-range weight * attn * g (g = 1)
+    g = torch.ones_like(out)
+    gv, gl, ga = ops.msda_backward(vd, ss.to(DEV), lsi.to(DEV), ld, ad, g)
+    rgv, rgl, rga = msda_oracle.msda_backward(v, ss, lsi, loc, attn, torch.ones(bs, nq, 256))
+    assert rel_err(gv.cpu(), rgv) < 1e-3
+    assert rel_err(ga.cpu(), rga) < 1e-3 and rel_err(gl.cpu(), rgl) < 1e-3

@@ -1,0 +1,165 @@
+"""CPU tests that pin the oracle: Oracle-S (C) and the torch restatement against the golden vectors
+made from the reference's own modules, against autograd of the grid_sample form, and -- where
+/root/reference is mounted -- against the reference modules directly."""
+import numpy as np
+import pytest
+import torch
+
+from bevformer_b200 import synthetic as syn
+from oracle import mmcv_stub, msda_oracle, torch_ref
+from tests.util import fixed_projection, golden, max_err, msda_case_inputs, stats, stats_close
+
+OP_CASES = ["kat", "kat_oob", "config0", "pyramid"]
+
+
+@pytest.mark.parametrize("case", OP_CASES)
+def test_oracle_s_matches_golden(case):
+    g = golden("msda_" + case)
+    v, ss, lsi, loc, attn = msda_case_inputs(g, torch.float64)
+    out = msda_oracle.msda_forward(v, ss, lsi, loc, attn)
+    rq, rs = g["rows_q"], g["rows_s"]
+    assert max_err(out[:, rq], g["out_rows"]) < 1e-6          # golden rows are stored as fp32
+    assert stats_close(stats(out), g["out_stats"], 1e-9)
+    gv, gl, ga = msda_oracle.msda_backward(v, ss, lsi, loc, attn,
+                                           fixed_projection(out.shape, dtype=torch.float64))
+    assert max_err(gv[:, rs], g["grad_value_rows"]) < 1e-5
+    assert max_err(gl[:, rq], g["grad_loc_rows"]) < 1e-4
+    assert max_err(ga[:, rq], g["grad_attn_rows"]) < 1e-5
+    assert stats_close(stats(gv), g["grad_value_stats"], 1e-9)
+    assert stats_close(stats(gl), g["grad_loc_stats"], 1e-9)
+    assert stats_close(stats(ga), g["grad_attn_stats"], 1e-9)
+
+
+def test_oracle_s_fp32_against_fp64():
+    g = golden("msda_pyramid")
+    v, ss, lsi, loc, attn = msda_case_inputs(g, torch.float32)
+    out = msda_oracle.msda_forward(v, ss, lsi, loc, attn)
+    assert out.dtype == torch.float32
+    assert max_err(out[:, g["rows_q"]], g["out_rows"]) < 2e-5
+
+
+@pytest.mark.parametrize("dim", [4, 30, 32, 64, 71])   # mmcv's gradcheck channel list
+def test_oracle_s_equals_grid_sample_autograd(dim):
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(2, [(6, 4), (3, 2)], 7, 2, dim, 2, seed=dim,
+                                                 dtype=torch.float64, loc_range=(-0.2, 1.2))
+    v.requires_grad_(); loc.requires_grad_(); attn.requires_grad_()
+    ref = torch_ref.msda_grid_sample(v, ss, loc, attn)
+    gout = torch.randn_like(ref)
+    ref.backward(gout)
+    out = msda_oracle.msda_forward(v, ss, lsi, loc, attn)
+    gv, gl, ga = msda_oracle.msda_backward(v, ss, lsi, loc, attn, gout)
+    assert max_err(out, ref) < 1e-13
+    assert max_err(gv, v.grad) < 1e-13
+    assert max_err(gl, loc.grad) < 1e-11
+    assert max_err(ga, attn.grad) < 1e-13
+
+
+def test_oracle_s_gradcheck():
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(1, [(5, 4), (3, 2)], 3, 2, 4, 2, seed=1,
+                                                 dtype=torch.float64, loc_range=(0.05, 0.95))
+    v.requires_grad_(); loc.requires_grad_(); attn.requires_grad_()
+    fn = lambda a, b, c: msda_oracle.MSDAOracleFunction.apply(a, ss, lsi, b, c, 64)
+    assert torch.autograd.gradcheck(fn, (v, loc, attn), eps=1e-6, atol=1e-4, rtol=1e-3,
+                                    nondet_tol=0.0)
+
+
+def test_oracle_s_properties():
+    ss = torch.tensor([[4, 5]]); lsi = torch.tensor([0])
+    value = torch.randn(1, 20, 1, 8, dtype=torch.float64)
+    # integer pixel centres reproduce value exactly
+    ys, xs = torch.meshgrid(torch.arange(4, dtype=torch.float64),
+                            torch.arange(5, dtype=torch.float64), indexing="ij")
+    loc = torch.stack([(xs + 0.5) / 5, (ys + 0.5) / 4], -1).reshape(1, 20, 1, 1, 1, 2)
+    out = msda_oracle.msda_forward(value, ss, lsi, loc, torch.ones(1, 20, 1, 1, 1).double())
+    assert max_err(out, value.view(1, 20, 8)) < 1e-14
+    # locations at least one pixel outside contribute exactly zero (x <= -1 px or >= W px)
+    far = torch.tensor([[-0.5 / 5 - 1e-9, 0.5], [1.0 + 0.5 / 5, 0.5], [0.5, -0.125 - 1e-9],
+                        [0.5, 1.125], [1e9, 0.5], [0.5, -1e9]], dtype=torch.float64)
+    out = msda_oracle.msda_forward(value, ss, lsi, far.view(1, 6, 1, 1, 1, 2),
+                                   torch.ones(1, 6, 1, 1, 1).double())
+    assert out.abs().max().item() == 0.0
+    # empty query set
+    out = msda_oracle.msda_forward(value, ss, lsi, loc[:, :0], torch.ones(1, 0, 1, 1, 1).double())
+    assert out.shape == (1, 0, 8)
+
+
+ENC_CASES = [("toy", "toy", 1, True), ("toy_bs2", "toy", 2, True), ("toy_noprev", "toy", 1, False),
+             ("tiny", "tiny", 1, True), ("tiny_noprev", "tiny", 1, False)]
+
+
+def _enc_inputs(workload, bs, with_prev, seed=0, dtype=torch.float32):
+    w = syn.WORKLOADS[workload]
+    inp = syn.make_encoder_inputs(w, bs=bs, seed=seed, with_prev=with_prev, dtype=dtype)
+    if bs > 1:
+        g = torch.Generator().manual_seed(99)
+        inp.feat = inp.feat + (0.5 * torch.randn(inp.feat.shape, generator=g)).to(dtype)
+        inp.bev_query = inp.bev_query + (0.1 * torch.randn(inp.bev_query.shape, generator=g)).to(dtype)
+    return w, inp
+
+
+@pytest.mark.parametrize("name,workload,bs,with_prev", ENC_CASES)
+@pytest.mark.parametrize("use_c", [False, True])
+def test_restatement_matches_golden(name, workload, bs, with_prev, use_c):
+    g = golden("encoder_" + name)
+    w, inp = _enc_inputs(workload, bs, with_prev)
+    sd = syn.make_state_dict(w)
+    with torch.no_grad():
+        out = torch_ref.encoder_forward(sd, w.num_layers, inp.bev_query, inp.feat,
+                                        use_c_oracle=use_c, **inp.kwargs())
+    assert max_err(out[:, g["rows_q"]], g["out_rows"]) < 2e-4
+    if "out_full" in g:
+        assert max_err(out, g["out_full"]) < 2e-4
+    assert stats_close(stats(out), g["out_stats"], 1e-4)
+
+
+def test_restatement_backward_matches_golden():
+    g = golden("encoder_toy")
+    w, inp = _enc_inputs("toy", 1, True)
+    sd = {k: v.clone().requires_grad_(True) for k, v in syn.make_state_dict(w).items()}
+    inp.bev_query.requires_grad_(True); inp.feat.requires_grad_(True)
+    out = torch_ref.encoder_forward(sd, w.num_layers, inp.bev_query, inp.feat, use_c_oracle=True,
+                                    **inp.kwargs())
+    (out * fixed_projection(out.shape)).sum().backward()
+    assert max_err(inp.bev_query.grad[g["rows_q"]], g["grad_query_rows"]) < 5e-4
+    assert max_err(inp.feat.grad[:, g["rows_s"]], g["grad_feat_rows"]) < 5e-4
+    for k, p in sd.items():
+        assert stats_close(stats(p.grad), g["gstat:" + k], 2e-3), k
+
+
+@pytest.mark.skipif(not mmcv_stub.reference_available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("bs,with_prev", [(1, True), (2, True), (1, False)])
+def test_restatement_vs_reference_fp64(bs, with_prev):
+    """Direct check against the reference's unmodified modules, in fp64 (no rounding slack)."""
+    w, inp = _enc_inputs("toy", bs, with_prev, dtype=torch.float64)
+    enc = mmcv_stub.build_reference_encoder(encoder_cfg=syn.encoder_cfg(w)).eval().double()
+    sd = syn.make_state_dict(w, dtype=torch.float64)
+    enc.load_state_dict(sd)
+    with torch.no_grad():
+        ref = enc(inp.bev_query, inp.feat, inp.feat, **inp.kwargs())
+        out = torch_ref.encoder_forward(sd, w.num_layers, inp.bev_query, inp.feat, **inp.kwargs())
+    # point_sampling runs in fp32 in both (encoder.py:87-93); everything else is fp64
+    assert max_err(out, ref) < 1e-9
+
+
+@pytest.mark.skipif(not mmcv_stub.reference_available(), reason="/root/reference not mounted")
+def test_state_dict_layout_equals_reference():
+    for name in ("tiny", "small", "base"):
+        w = syn.WORKLOADS[name]
+        enc = mmcv_stub.build_reference_encoder(w.config_file)
+        ref_sd, sd = enc.state_dict(), syn.make_state_dict(w)
+        assert list(sd.keys()) == list(ref_sd.keys()) or set(sd) == set(ref_sd)
+        for k in sd:
+            assert sd[k].shape == ref_sd[k].shape, k
+        sd0 = syn.make_state_dict(w, trained_like=False)
+        for k in sd0:   # the deterministic reference initialisers
+            if "sampling_offsets" in k or "attention_weights" in k or "norms" in k:
+                assert torch.equal(sd0[k], ref_sd[k]), k
+
+
+def test_rig_hit_counts():
+    """the synthetic rig gives these per-camera hit counts at base."""
+    w = syn.WORKLOADS["base"]
+    ref3d = torch_ref.reference_points_3d(w.bev_h, w.bev_w, 8.0, 4, 1, torch.float32)
+    _, mask = torch_ref.point_sampling(ref3d, syn.PC_RANGE, syn.make_img_metas(w))
+    hits = [(mask[i, 0].sum(-1) > 0).sum().item() for i in range(6)]
+    assert hits == [6071, 7481, 7417, 9507, 7049, 6986]

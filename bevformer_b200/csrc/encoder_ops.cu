@@ -1,0 +1,598 @@
+// Fused memory-bound pieces of one BEVFormer encoder layer (everything between the GEMMs and the
+// sampler).  Each kernel replaces a run of ATen launches in the reference; see the per-function
+// comments in include/bevformer_b200.h for the Python lines.  All are HBM-bound streaming kernels:
+// 16 B vector accesses, one pass over each tensor, fp32 math.
+#include "common.cuh"
+
+namespace bevf {
+
+constexpr int kEThreads = 256;
+constexpr int kMaxLP = 64;        // num_levels * num_points per head handled in registers
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SCA sampling-point preparation
+// raw row (per query): [ offsets (M, L, P, 2) | logits (M, L*P) ]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEThreads)
+sca_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref_cam,
+             const int *__restrict__ pair_q, const int *__restrict__ pair_cam,
+             const int64_t *__restrict__ level_hw, float *__restrict__ loc, float *__restrict__ attn,
+             int B, int Nq, int R, int M, int L, int P, int D, int ncam) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * R * M;
+    if (t >= total) return;
+    const int m = (int)(t % M);
+    const long long br = t / M;
+    const int r = (int)(br % R), b = (int)(br / R);
+    const int q = pair_q[r], cam = pair_cam[r];
+    const int LP = L * P, nout = M * LP * 3;
+    const float *rq = raw + ((long long)b * Nq + q) * nout;
+    const float *off = rq + (long long)m * LP * 2;
+    const float *lg = rq + (long long)M * LP * 2 + (long long)m * LP;
+    const float *rc = ref_cam + (((long long)cam * B + b) * Nq + q) * D * 2;
+    // softmax over the L*P logits of this head
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+    for (int k = 0; k < LP; ++k) sum += __expf(lg[k] - mx);
+    const float inv = 1.f / sum;
+    float *lo = loc + t * LP * 2;
+    float *at = attn + t * LP;
+    for (int l = 0; l < L; ++l) {
+        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        for (int p = 0; p < P; ++p) {
+            const int k = l * P + p, z = p % D;          // point p uses Z-anchor p mod D (quirk 3)
+            const float2 o = *reinterpret_cast<const float2 *>(off + 2 * k);
+            const float2 rf = *reinterpret_cast<const float2 *>(rc + 2 * z);
+            *reinterpret_cast<float2 *>(lo + 2 * k) = make_float2(rf.x + o.x * iw, rf.y + o.y * ih);
+            at[k] = __expf(lg[k] - mx) * inv;
+        }
+    }
+}
+
+// d_raw for every query: sums over the cameras that see it (pair_of[cam][q] = row or -1)
+__global__ void __launch_bounds__(kEThreads)
+sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
+             const float *__restrict__ grad_attn, const int *__restrict__ pair_of,
+             const int64_t *__restrict__ level_hw, float *__restrict__ d_raw, int B, int Nq, int R,
+             int M, int L, int P, int ncam) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Nq * M;
+    if (t >= total) return;
+    const int m = (int)(t % M);
+    const long long bq = t / M;
+    const int q = (int)(bq % Nq), b = (int)(bq / Nq);
+    const int LP = L * P, nout = M * LP * 3;
+    const float *lg = raw + bq * nout + (long long)M * LP * 2 + (long long)m * LP;
+    float *d_off = d_raw + bq * nout + (long long)m * LP * 2;
+    float *d_lg = d_raw + bq * nout + (long long)M * LP * 2 + (long long)m * LP;
+    int rows[16];
+    int n = 0;
+    for (int c = 0; c < ncam && c < 16; ++c) {
+        const int r = pair_of[(long long)c * Nq + q];
+        if (r >= 0) rows[n++] = r;
+    }
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+    for (int k = 0; k < LP; ++k) sum += __expf(lg[k] - mx);
+    const float inv = 1.f / sum;
+    // dot = sum_k a_k * Ga_k
+    float dot = 0.f;
+    for (int k = 0; k < LP; ++k) {
+        float ga = 0.f;
+        for (int i = 0; i < n; ++i) ga += grad_attn[(((long long)b * R + rows[i]) * M + m) * LP + k];
+        dot += __expf(lg[k] - mx) * inv * ga;
+    }
+    for (int l = 0; l < L; ++l) {
+        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        for (int p = 0; p < P; ++p) {
+            const int k = l * P + p;
+            float ga = 0.f, gx = 0.f, gy = 0.f;
+            for (int i = 0; i < n; ++i) {
+                const long long s = (((long long)b * R + rows[i]) * M + m) * LP + k;
+                ga += grad_attn[s];
+                const float2 g2 = *reinterpret_cast<const float2 *>(grad_loc + 2 * s);
+                gx += g2.x; gy += g2.y;
+            }
+            const float a = __expf(lg[k] - mx) * inv;
+            d_lg[k] = a * (ga - dot);
+            *reinterpret_cast<float2 *>(d_off + 2 * k) = make_float2(gx * iw, gy * ih);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TSA sampling-point preparation.  raw row: [ offsets (M, 2, L, P, 2) | logits (M, 2, L*P) ]
+// out rows ordered (b, queue j, q): loc (B*2, Nq, M, L, P, 2), attn (B*2, Nq, M, L, P)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEThreads)
+tsa_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref2d,
+             const int64_t *__restrict__ level_hw, float *__restrict__ loc, float *__restrict__ attn,
+             int B, int Nq, int M, int L, int P) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Nq * M * 2;
+    if (t >= total) return;
+    const int j = (int)(t & 1);
+    const long long t2 = t >> 1;
+    const int m = (int)(t2 % M);
+    const long long bq = t2 / M;
+    const int q = (int)(bq % Nq), b = (int)(bq / Nq);
+    const int LP = L * P, nout = M * 2 * LP * 3;
+    const float *off = raw + bq * nout + ((long long)m * 2 + j) * LP * 2;
+    const float *lg = raw + bq * nout + (long long)M * 2 * LP * 2 + ((long long)m * 2 + j) * LP;
+    const long long orow = (((long long)b * 2 + j) * Nq + q);
+    const float *rf = ref2d + orow * L * 2;
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+    for (int k = 0; k < LP; ++k) sum += __expf(lg[k] - mx);
+    const float inv = 1.f / sum;
+    float *lo = loc + (orow * M + m) * LP * 2;
+    float *at = attn + (orow * M + m) * LP;
+    for (int l = 0; l < L; ++l) {
+        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        const float rx = rf[2 * l], ry = rf[2 * l + 1];
+        for (int p = 0; p < P; ++p) {
+            const int k = l * P + p;
+            const float2 o = *reinterpret_cast<const float2 *>(off + 2 * k);
+            *reinterpret_cast<float2 *>(lo + 2 * k) = make_float2(rx + o.x * iw, ry + o.y * ih);
+            at[k] = __expf(lg[k] - mx) * inv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kEThreads)
+tsa_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
+             const float *__restrict__ grad_attn, const int64_t *__restrict__ level_hw,
+             float *__restrict__ d_raw, int B, int Nq, int M, int L, int P) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Nq * M * 2;
+    if (t >= total) return;
+    const int j = (int)(t & 1);
+    const long long t2 = t >> 1;
+    const int m = (int)(t2 % M);
+    const long long bq = t2 / M;
+    const int q = (int)(bq % Nq), b = (int)(bq / Nq);
+    const int LP = L * P, nout = M * 2 * LP * 3;
+    const long long o_off = bq * nout + ((long long)m * 2 + j) * LP * 2;
+    const long long o_lg = bq * nout + (long long)M * 2 * LP * 2 + ((long long)m * 2 + j) * LP;
+    const float *lg = raw + o_lg;
+    const long long orow = (((long long)b * 2 + j) * Nq + q);
+    const float *gl = grad_loc + (orow * M + m) * LP * 2;
+    const float *ga = grad_attn + (orow * M + m) * LP;
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+    for (int k = 0; k < LP; ++k) sum += __expf(lg[k] - mx);
+    const float inv = 1.f / sum;
+    float dot = 0.f;
+    for (int k = 0; k < LP; ++k) dot += __expf(lg[k] - mx) * inv * ga[k];
+    for (int l = 0; l < L; ++l) {
+        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        for (int p = 0; p < P; ++p) {
+            const int k = l * P + p;
+            const float a = __expf(lg[k] - mx) * inv;
+            d_raw[o_lg + k] = a * (ga[k] - dot);
+            const float2 g2 = *reinterpret_cast<const float2 *>(gl + 2 * k);
+            *reinterpret_cast<float2 *>(d_raw + o_off + 2 * k) = make_float2(g2.x * iw, g2.y * ih);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C channels with fused residual add and an optional second output y + pos.
+// One warp per row; a lane holds C/32 channels in registers (C <= 1024, C % 128 == 0 fast path for
+// 16 B accesses).  Statistics in fp32; eps inside the sqrt.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(kEThreads)
+layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ gamma,
+              const float *__restrict__ beta, const T *__restrict__ pos, T *__restrict__ y,
+              T *__restrict__ y2, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+              long long rows, float eps) {
+    constexpr int PER = C / 32;                 // channels per lane (8 for C = 256)
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    static_assert(PER % VEC == 0, "C must be a multiple of 32 * VEC");
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (kEThreads / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i += VEC) {
+        const int c = (i / VEC) * 32 * VEC + lane * VEC;
+        float tmp[VEC];
+        load_vec<T, VEC>(x + row * C + c, tmp);
+        if (res) {
+            float r2[VEC];
+            load_vec<T, VEC>(res + row * C + c, r2);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) tmp[k] += r2[k];
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[i + k] = tmp[k];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.f / C);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; s2 += d * d; }
+    const float rstd = rsqrtf(warp_sum(s2) * (1.f / C) + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i += VEC) {
+        const int c = (i / VEC) * 32 * VEC + lane * VEC;
+        float o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            o[k] = (v[i + k] - mean) * rstd * __ldg(gamma + c + k) + __ldg(beta + c + k);
+        store_vec<T, VEC>(y + row * C + c, o);
+        if (y2) {
+            float pz[VEC];
+            load_vec<T, VEC>(pos + row * C + c, pz);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) pz[k] += o[k];
+            store_vec<T, VEC>(y2 + row * C + c, pz);
+        }
+    }
+}
+
+// Backward.  xin = x (+ res) is recomputed from the saved inputs; dy2 (grad of the y + pos output) is
+// added to dy.  dx is written once (it is also the residual's gradient); dgamma/dbeta accumulate
+// into fp32 buffers through one atomicAdd per channel per CTA.
+template <typename T, int C>
+__global__ void __launch_bounds__(kEThreads)
+layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ gamma,
+              const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+              const T *__restrict__ dy, const T *__restrict__ dy2, T *__restrict__ dx,
+              float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows,
+              int rows_per_cta) {
+    constexpr int PER = C / 32;
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    __shared__ float s_dg[C], s_db[C];
+    for (int i = threadIdx.x; i < C; i += kEThreads) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float adg[PER], adb[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
+    const long long row0 = (long long)blockIdx.x * rows_per_cta;
+    for (long long row = row0 + warp; row < row0 + rows_per_cta && row < rows; row += kEThreads / 32) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float xh[PER], g[PER];
+#pragma unroll
+        for (int i = 0; i < PER; i += VEC) {
+            const int c = (i / VEC) * 32 * VEC + lane * VEC;
+            float tx[VEC], tg[VEC];
+            load_vec<T, VEC>(x + row * C + c, tx);
+            if (res) {
+                float r2[VEC];
+                load_vec<T, VEC>(res + row * C + c, r2);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) tx[k] += r2[k];
+            }
+            load_vec<T, VEC>(dy + row * C + c, tg);
+            if (dy2) {
+                float t2[VEC];
+                load_vec<T, VEC>(dy2 + row * C + c, t2);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) tg[k] += t2[k];
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { xh[i + k] = (tx[k] - mean) * rstd; g[i + k] = tg[k]; }
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int c = (i / VEC) * 32 * VEC + lane * VEC + (i % VEC);
+            const float gg = g[i] * __ldg(gamma + c);
+            s1 += gg; s2 += gg * xh[i];
+            adg[i] += g[i] * xh[i]; adb[i] += g[i];
+        }
+        s1 = warp_sum(s1) * (1.f / C); s2 = warp_sum(s2) * (1.f / C);
+#pragma unroll
+        for (int i = 0; i < PER; i += VEC) {
+            const int c = (i / VEC) * 32 * VEC + lane * VEC;
+            float o[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                o[k] = rstd * (g[i + k] * __ldg(gamma + c + k) - s1 - xh[i + k] * s2);
+            store_vec<T, VEC>(dx + row * C + c, o);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = (i / VEC) * 32 * VEC + lane * VEC + (i % VEC);
+        atomicAdd(&s_dg[c], adg[i]);
+        atomicAdd(&s_db[c], adb[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += kEThreads) {
+        atomicAdd(dgamma + i, s_dg[i]);
+        atomicAdd(dbeta + i, s_db[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SCA combine: slots[b,q,:] = inv_count[b,q] * sum over cameras seeing q of out[b*R + r, :]
+// and its backward g_out[b*R + r, :] = inv_count[b, q_r] * g_slots[b, q_r, :]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEThreads)
+sca_combine_fwd(const T *__restrict__ out, const int *__restrict__ pair_of,
+                const float *__restrict__ inv_count, T *__restrict__ slots, int B, int Nq, int R,
+                int C, int ncam) {
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    const int per_row = C / VEC;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * Nq * per_row) return;
+    const int cv = (int)(t % per_row);
+    const long long bq = t / per_row;
+    const int q = (int)(bq % Nq), b = (int)(bq / Nq);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int c = 0; c < ncam; ++c) {
+        const int r = __ldg(pair_of + (long long)c * Nq + q);
+        if (r < 0) continue;
+        float v[VEC];
+        load_vec<T, VEC>(out + ((long long)b * R + r) * C + cv * VEC, v);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += v[k];
+    }
+    const float ic = inv_count[bq];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] *= ic;
+    store_vec<T, VEC>(slots + bq * C + cv * VEC, acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEThreads)
+sca_combine_bwd(const T *__restrict__ g_slots, const int *__restrict__ pair_q,
+                const float *__restrict__ inv_count, T *__restrict__ g_out, int B, int Nq, int R,
+                int C) {
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    const int per_row = C / VEC;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * R * per_row) return;
+    const int cv = (int)(t % per_row);
+    const long long br = t / per_row;
+    const int r = (int)(br % R), b = (int)(br / R);
+    const int q = __ldg(pair_q + r);
+    const float ic = inv_count[(long long)b * Nq + q];
+    float v[VEC];
+    load_vec<T, VEC>(g_slots + ((long long)b * Nq + q) * C + cv * VEC, v);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] *= ic;
+    store_vec<T, VEC>(g_out + br * C + cv * VEC, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// point sampling: lidar -> image projection of the pillar anchors + in-view mask, fp32
+// ------------------------------------------------------------------------------------------------
+struct PointSamplingParams {
+    float pc[6];
+    float zs[16];      // normalised pillar heights (D of them)
+    float img_h, img_w;
+};
+
+__global__ void __launch_bounds__(kEThreads)
+point_sampling_kernel(const float *__restrict__ lidar2img, PointSamplingParams prm,
+                      float *__restrict__ ref_cam, unsigned char *__restrict__ mask, int B,
+                      int ncam, int H, int W, int D) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Nq = H * W;
+    const long long total = (long long)ncam * B * Nq * D;
+    if (t >= total) return;
+    const int d = (int)(t % D);
+    long long u = t / D;
+    const int q = (int)(u % Nq); u /= Nq;
+    const int b = (int)(u % B);
+    const int cam = (int)(u / B);
+    const int i = q / W, j = q % W;
+    // reference points exactly as torch.linspace(0.5, n - 0.5, n) / n builds them (encoder.py:62-67)
+    const float xn = ((float)j + 0.5f) / (float)W, yn = ((float)i + 0.5f) / (float)H, zn = prm.zs[d];
+    const float X = xn * (prm.pc[3] - prm.pc[0]) + prm.pc[0];
+    const float Y = yn * (prm.pc[4] - prm.pc[1]) + prm.pc[1];
+    const float Z = zn * (prm.pc[5] - prm.pc[2]) + prm.pc[2];
+    const float *m4 = lidar2img + ((long long)b * ncam + cam) * 16;
+    // plain (non-fused) fp32 multiply-adds in row order, like a 4x4 @ 4x1 matmul with TF32 off
+    const float cx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m4[0], X), __fmul_rn(m4[1], Y)), __fmul_rn(m4[2], Z)), m4[3]);
+    const float cy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m4[4], X), __fmul_rn(m4[5], Y)), __fmul_rn(m4[6], Z)), m4[7]);
+    const float cz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m4[8], X), __fmul_rn(m4[9], Y)), __fmul_rn(m4[10], Z)), m4[11]);
+    const float eps = 1e-5f;
+    bool ok = cz > eps;
+    const float dz = fmaxf(cz, eps);
+    const float px = __fdiv_rn(__fdiv_rn(cx, dz), prm.img_w), py = __fdiv_rn(__fdiv_rn(cy, dz), prm.img_h);
+    ok = ok && (py > 0.f) && (py < 1.f) && (px < 1.f) && (px > 0.f);
+    const long long o = (((long long)cam * B + b) * Nq + q) * D + d;
+    reinterpret_cast<float2 *>(ref_cam)[o] = make_float2(px, py);
+    mask[o] = ok ? 1 : 0;
+}
+
+}  // namespace bevf
+
+using namespace bevf;
+
+#define BEVF_REQUIRE(cond, who, msg) do { if (!(cond)) return fail("%s: " msg, who); } while (0)
+
+static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" int bevf_sca_prep_forward(const float *raw, const float *ref_cam, const int32_t *pair_q,
+                                     const int32_t *pair_cam, const int64_t *level_hw, float *loc,
+                                     float *attn, int B, int Nq, int R, int M, int L, int P, int D,
+                                     int ncam, void *stream) {
+    const char *who = "bevf_sca_prep_forward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && R >= 0 && M > 0 && L > 0 && P > 0 && D > 0 && ncam > 0, who, "bad dimension");
+    BEVF_REQUIRE(P % D == 0, who, "num_points must be a multiple of the number of Z anchors");
+    const long long total = (long long)B * R * M;
+    if (total == 0) return 0;
+    BEVF_REQUIRE(raw && ref_cam && pair_q && pair_cam && level_hw && loc && attn, who, "null pointer argument");
+    sca_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+        raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, M, L, P, D, ncam);
+    return check_launch(who);
+}
+
+extern "C" int bevf_sca_prep_backward(const float *raw, const float *grad_loc,
+                                      const float *grad_attn, const int32_t *pair_of,
+                                      const int64_t *level_hw, float *d_raw, int B, int Nq, int R,
+                                      int M, int L, int P, int ncam, void *stream) {
+    const char *who = "bevf_sca_prep_backward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && R >= 0 && M > 0 && L > 0 && P > 0 && ncam > 0 && ncam <= 16, who, "bad dimension (ncam <= 16)");
+    const long long total = (long long)B * Nq * M;
+    if (total == 0) return 0;
+    BEVF_REQUIRE(raw && pair_of && level_hw && d_raw && (R == 0 || (grad_loc && grad_attn)), who, "null pointer argument");
+    sca_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+        raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, M, L, P, ncam);
+    return check_launch(who);
+}
+
+extern "C" int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const int64_t *level_hw,
+                                     float *loc, float *attn, int B, int Nq, int M, int L, int P,
+                                     void *stream) {
+    const char *who = "bevf_tsa_prep_forward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && M > 0 && L > 0 && P > 0, who, "bad dimension");
+    const long long total = (long long)B * Nq * M * 2;
+    if (total == 0) return 0;
+    BEVF_REQUIRE(raw && ref2d && level_hw && loc && attn, who, "null pointer argument");
+    tsa_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+        raw, ref2d, level_hw, loc, attn, B, Nq, M, L, P);
+    return check_launch(who);
+}
+
+extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
+                                      const float *grad_attn, const int64_t *level_hw, float *d_raw,
+                                      int B, int Nq, int M, int L, int P, void *stream) {
+    const char *who = "bevf_tsa_prep_backward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && M > 0 && L > 0 && P > 0, who, "bad dimension");
+    const long long total = (long long)B * Nq * M * 2;
+    if (total == 0) return 0;
+    BEVF_REQUIRE(raw && grad_loc && grad_attn && level_hw && d_raw, who, "null pointer argument");
+    tsa_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+        raw, grad_loc, grad_attn, level_hw, d_raw, B, Nq, M, L, P);
+    return check_launch(who);
+}
+
+template <typename T>
+static int ln_fwd_t(const char *who, const void *x, const void *res, const float *gamma,
+                    const float *beta, const void *pos, void *y, void *y2, float *mean, float *rstd,
+                    long long rows, int C, float eps, cudaStream_t st) {
+    const unsigned grid = blocks_for(rows, kEThreads / 32);
+    if (C == 256)
+        layernorm_fwd<T, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps);
+    else if (C == 512)
+        layernorm_fwd<T, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps);
+    else
+        return fail("%s: embed_dims must be 256 or 512", who);
+    return check_launch(who);
+}
+
+extern "C" int bevf_layernorm_forward(const void *x, const void *residual, const float *gamma,
+                                      const float *beta, const void *pos, void *y, void *y_plus_pos,
+                                      float *mean, float *rstd, int64_t rows, int C, float eps,
+                                      int dtype, void *stream) {
+    const char *who = "bevf_layernorm_forward";
+    BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
+    if (rows == 0) return 0;
+    BEVF_REQUIRE(x && gamma && beta && y, who, "null pointer argument");
+    BEVF_REQUIRE((y_plus_pos == nullptr) == (pos == nullptr), who, "pos and y_plus_pos go together");
+    if (dtype == BEVF_DTYPE_F32) return ln_fwd_t<float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, (cudaStream_t)stream);
+    if (dtype == BEVF_DTYPE_BF16) return ln_fwd_t<bf16>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, (cudaStream_t)stream);
+    return fail("%s: unsupported dtype code", who);
+}
+
+template <typename T>
+static int ln_bwd_t(const char *who, const void *x, const void *res, const float *gamma,
+                    const float *mean, const float *rstd, const void *dy, const void *dy2, void *dx,
+                    float *dgamma, float *dbeta, long long rows, int C, cudaStream_t st) {
+    // ~4 CTAs per SM worth of row chunks keeps the per-channel atomics few
+    int rows_per_cta = (int)((rows + 148 * 4 - 1) / (148 * 4));
+    rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
+    if (rows_per_cta < 8) rows_per_cta = 8;
+    const unsigned grid = blocks_for(rows, rows_per_cta);
+    if (C == 256)
+        layernorm_bwd<T, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, dgamma, dbeta, rows, rows_per_cta);
+    else if (C == 512)
+        layernorm_bwd<T, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, dgamma, dbeta, rows, rows_per_cta);
+    else
+        return fail("%s: embed_dims must be 256 or 512", who);
+    return check_launch(who);
+}
+
+extern "C" int bevf_layernorm_backward(const void *x, const void *residual, const float *gamma,
+                                       const float *mean, const float *rstd, const void *dy,
+                                       const void *dy_plus_pos, void *dx, float *dgamma,
+                                       float *dbeta, int64_t rows, int C, int dtype, void *stream) {
+    const char *who = "bevf_layernorm_backward";
+    BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
+    if (rows == 0) return 0;
+    BEVF_REQUIRE(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, who, "null pointer argument");
+    if (dtype == BEVF_DTYPE_F32) return ln_bwd_t<float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dgamma, dbeta, rows, C, (cudaStream_t)stream);
+    if (dtype == BEVF_DTYPE_BF16) return ln_bwd_t<bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dgamma, dbeta, rows, C, (cudaStream_t)stream);
+    return fail("%s: unsupported dtype code", who);
+}
+
+extern "C" int bevf_sca_combine_forward(const void *out, const int32_t *pair_of,
+                                        const float *inv_count, void *slots, int B, int Nq, int R,
+                                        int C, int ncam, int dtype, void *stream) {
+    const char *who = "bevf_sca_combine_forward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && R >= 0 && C > 0 && C % 8 == 0 && ncam > 0, who, "bad dimension");
+    if ((long long)B * Nq == 0) return 0;
+    BEVF_REQUIRE(pair_of && inv_count && slots && (R == 0 || out), who, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BEVF_DTYPE_F32) {
+        sca_combine_fwd<float><<<blocks_for((long long)B * Nq * (C / 4), kEThreads), kEThreads, 0, st>>>((const float *)out, pair_of, inv_count, (float *)slots, B, Nq, R, C, ncam);
+    } else if (dtype == BEVF_DTYPE_BF16) {
+        sca_combine_fwd<bf16><<<blocks_for((long long)B * Nq * (C / 8), kEThreads), kEThreads, 0, st>>>((const bf16 *)out, pair_of, inv_count, (bf16 *)slots, B, Nq, R, C, ncam);
+    } else {
+        return fail("%s: unsupported dtype code", who);
+    }
+    return check_launch(who);
+}
+
+extern "C" int bevf_sca_combine_backward(const void *g_slots, const int32_t *pair_q,
+                                         const float *inv_count, void *g_out, int B, int Nq, int R,
+                                         int C, int dtype, void *stream) {
+    const char *who = "bevf_sca_combine_backward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && R >= 0 && C > 0 && C % 8 == 0, who, "bad dimension");
+    if ((long long)B * R == 0) return 0;
+    BEVF_REQUIRE(g_slots && pair_q && inv_count && g_out, who, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BEVF_DTYPE_F32) {
+        sca_combine_bwd<float><<<blocks_for((long long)B * R * (C / 4), kEThreads), kEThreads, 0, st>>>((const float *)g_slots, pair_q, inv_count, (float *)g_out, B, Nq, R, C);
+    } else if (dtype == BEVF_DTYPE_BF16) {
+        sca_combine_bwd<bf16><<<blocks_for((long long)B * R * (C / 8), kEThreads), kEThreads, 0, st>>>((const bf16 *)g_slots, pair_q, inv_count, (bf16 *)g_out, B, Nq, R, C);
+    } else {
+        return fail("%s: unsupported dtype code", who);
+    }
+    return check_launch(who);
+}
+
+extern "C" int bevf_point_sampling(const float *lidar2img, const float *pc_range,
+                                   const float *z_norm, float img_h, float img_w, float *ref_cam,
+                                   uint8_t *bev_mask, int B, int ncam, int bev_h, int bev_w, int D,
+                                   void *stream) {
+    const char *who = "bevf_point_sampling";
+    BEVF_REQUIRE(B >= 0 && ncam > 0 && bev_h > 0 && bev_w > 0 && D > 0 && D <= 16, who, "bad dimension (D <= 16)");
+    const long long total = (long long)ncam * B * bev_h * bev_w * D;
+    if (total == 0) return 0;
+    BEVF_REQUIRE(lidar2img && pc_range && z_norm && ref_cam && bev_mask, who, "null pointer argument");
+    PointSamplingParams prm;
+    for (int i = 0; i < 6; ++i) prm.pc[i] = pc_range[i];     // HOST arrays
+    for (int i = 0; i < D; ++i) prm.zs[i] = z_norm[i];
+    prm.img_h = img_h; prm.img_w = img_w;
+    point_sampling_kernel<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+        lidar2img, prm, ref_cam, bev_mask, B, ncam, bev_h, bev_w, D);
+    return check_launch(who);
+}

@@ -3,14 +3,25 @@
 //
 // Replaces the reference's native op (mmcv._ext.ms_deform_attn_{forward,backward}; call sites
 // projects/mmdet3d_plugin/bevformer/modules/multi_scale_deformable_attn_function.py:118-124 and
-// :150-160).  Arithmetic: SURVEY.md Appendix A.  This is HBM/L2-bound gather work: no tensor cores.
+// :150-160).  Arithmetic: SURVEY.md Appendix A.  This is gather/scatter work bound by L1/L2 and
+// instruction issue, not GEMM-shaped: no tensor cores.
 //
 // Mapping (head_dim == 32 fast path).  One (pixel, head) row of `value` is 32 contiguous channels:
 // 128 B in fp32, 64 B in bf16.  A lane owns 16 B of it (4 fp32 / 8 bf16 channels), so a row is
-// covered by 8 (fp32) or 4 (bf16) adjacent lanes and one warp works on 4 / 8 consecutive
-// (query, head) pairs at once.  Every corner fetch is therefore one fully-used 16 B vector load per
-// lane, a (query, head) pair's sampling locations / weights are read once per lane group, and the
-// output row is written with 16 B stores that are contiguous across the warp.
+// covered by LANES = 8 (fp32) or 4 (bf16) adjacent lanes and one warp works on G = 4 / 8 consecutive
+// (query, head) pairs at once.
+//   * Every corner fetch is one fully-used 16 B vector load per lane.
+//   * The per-sample scalar work (pixel coordinates, range test, bilinear weights x attention weight,
+//     corner addresses) is done ONCE per sample: in each round the LANES lanes of a group take LANES
+//     different samples, then hand {packed corner address, weights} round with __shfl_sync.
+//   * Samples that are out of view for every (query, head) pair of the warp are skipped with one
+//     ballot (in SCA all 8 heads of a query share the projected anchor, so whole anchors drop out).
+//   * bf16 storage: fp32 accumulation through fma.rn.f32.bf16 (SASS FHFMA.BF16), which reads bf16
+//     operands straight from register halves -- no unpack instructions.
+//   * backward: per sample only the four dot products <grad_out, corner> are formed per lane; they
+//     are reduce-scattered over the group so that the lane that produced the sample's scalars also
+//     finishes grad_loc / grad_attn.  grad_value is scattered with 16 B vector reductions
+//     (REDG.E.ADD.F32x4), never scalar atomics.
 #include "common.cuh"
 
 namespace bevf {
@@ -19,15 +30,16 @@ constexpr int kMaxLevels = 16;
 constexpr int kThreads = 256;
 
 struct Corner {
-    int off00, off01, off10, off11;   // element offsets of the four corners (clamped in range)
-    float w00, w01, w10, w11;         // bilinear weights, zero for corners outside the map
-    float f00, f01, f10, f11;         // 1 if the corner lies inside the map and the sample counts
+    int pidx;                         // pixel index y0c*W + x0c of the (clamped) top-left corner
+    int dx, dy;                       // 1 if the right / bottom neighbour is a distinct in-map pixel
+    float w00, w01, w10, w11;         // bilinear weights (zero for corners outside the map / skipped)
     float lx, ly;
+    float f00, f01, f10, f11;         // 1 if the corner lies inside the map and the sample counts
     bool valid;
 };
 
 // Range test in float BEFORE any int conversion: projected anchors behind a camera reach |x| ~ 1e9.
-__device__ __forceinline__ Corner make_corner(float locx, float locy, int H, int W, int pix_stride) {
+__device__ __forceinline__ Corner make_corner(float locx, float locy, int H, int W) {
     Corner c;
     float x = locx * (float)W - 0.5f, y = locy * (float)H - 0.5f;
     c.valid = (x > -1.f) && (y > -1.f) && (x < (float)W) && (y < (float)H);
@@ -45,11 +57,11 @@ __device__ __forceinline__ Corner make_corner(float locx, float locy, int H, int
     c.w01 = c.f01 * hy * c.lx;
     c.w10 = c.f10 * c.ly * hx;
     c.w11 = c.f11 * c.ly * c.lx;
-    const int x0c = max(x0, 0), x1c = min(x1, W - 1), y0c = max(y0, 0), y1c = min(y1, H - 1);
-    c.off00 = (y0c * W + x0c) * pix_stride;
-    c.off01 = (y0c * W + x1c) * pix_stride;
-    c.off10 = (y1c * W + x0c) * pix_stride;
-    c.off11 = (y1c * W + x1c) * pix_stride;
+    // Clamp into the map.  When x0 == -1 the only in-map column is x1 == 0: corner "00" then aliases
+    // pixel 0 with weight 0 and corner "01" must also address pixel 0, hence dx = 0 (same for y).
+    c.pidx = max(y0, 0) * W + max(x0, 0);
+    c.dx = (x0ok && x1ok) ? 1 : 0;
+    c.dy = (y0ok && y1ok) ? 1 : 0;
     return c;
 }
 
@@ -63,6 +75,83 @@ __device__ __forceinline__ void load_levels(const int64_t *level_hw, const int64
     __syncthreads();
 }
 
+// ---- per-storage-type math ---------------------------------------------------------------------
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+    float d;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ void split16(uint32_t u, unsigned short &lo, unsigned short &hi) {
+    asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(u));
+}
+
+template <typename T> struct Vec;          // 16 B of a row as loaded
+template <> struct Vec<float> {
+    float4 v;
+    static constexpr int N = 4;
+    __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void axpy(float w, float (&acc)[4]) const {
+        acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
+        acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+    }
+    __device__ __forceinline__ float dot(const float (&g)[4]) const {
+        return fmaf(g[0], v.x, fmaf(g[1], v.y, fmaf(g[2], v.z, g[3] * v.w)));
+    }
+};
+template <> struct Vec<bf16> {
+    uint4 v;
+    static constexpr int N = 8;
+    __device__ __forceinline__ void load(const bf16 *p) { v = __ldg(reinterpret_cast<const uint4 *>(p)); }
+    // acc += w * v with w already rounded to bf16 (products exact, fp32 accumulation)
+    __device__ __forceinline__ void axpy_h(unsigned short w, float (&acc)[8]) const {
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned short lo, hi;
+            split16(u[i], lo, hi);
+            acc[2 * i] = fhfma(lo, w, acc[2 * i]);
+            acc[2 * i + 1] = fhfma(hi, w, acc[2 * i + 1]);
+        }
+    }
+    // <g, v> with g given as packed bf16 (exact products)
+    __device__ __forceinline__ float dot_h(const uint4 &g) const {
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w}, q[4] = {g.x, g.y, g.z, g.w};
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned short lo, hi, glo, ghi;
+            split16(u[i], lo, hi);
+            split16(q[i], glo, ghi);
+            d = fhfma(lo, glo, d);
+            d = fhfma(hi, ghi, d);
+        }
+        return d;
+    }
+    // <g, v> with g in fp32
+    __device__ __forceinline__ float dot(const float (&g)[8]) const {
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            d = fmaf(g[2 * i], bf16_lo(u[i]), d);
+            d = fmaf(g[2 * i + 1], bf16_hi(u[i]), d);
+        }
+        return d;
+    }
+};
+
+template <int LANES> struct GroupMask;
+template <> struct GroupMask<4> { static constexpr unsigned kBits = 0x11111111u; };
+template <> struct GroupMask<8> { static constexpr unsigned kBits = 0x01010101u; };
+
+// level of flat sample index s (= s / P) without an integer division: magic = ceil(2^16 / P),
+// exact while s * P < 2^16 (checked on the host: L * P * P < 65536).
+__device__ __forceinline__ int level_of(int s, int magic) { return (s * magic) >> 16; }
+
+__device__ __forceinline__ int value_map_of(const int *row_map, long long row, int M, int Q) {
+    return row_map ? __ldg(row_map + row / M) : (int)(row / ((long long)M * Q));
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward, head_dim == 32
 // ------------------------------------------------------------------------------------------------
@@ -70,47 +159,79 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const int64_t *__restrict__ level_start, const float *__restrict__ loc,
-             const float *__restrict__ attn, TO *__restrict__ out, int S, int M, int Q, int L, int P,
+             const float *__restrict__ attn, TO *__restrict__ out,
+             const int *__restrict__ row_map, int S, int M, int Q, int L, int P, int magic,
              long long rows) {
-    constexpr int VEC = Row<T>::kVec, LANES = 32 / VEC, G = 32 / LANES;
+    constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
+    constexpr bool kHalf = (VEC == 8);
     __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
     load_levels(level_hw, level_start, L, s_h, s_w, s_start);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
-    const long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * G + grp;
-    if (row >= rows) return;
+    long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * G + grp;
+    const bool live = row < rows;                 // dead groups still take part in the shuffles
+    if (!live) row = rows - 1;
     const int m = (int)(row % M);
-    const int b = (int)(row / ((long long)M * Q));
+    const int b = value_map_of(row_map, row, M, Q);
     const int pix = M * 32;
+    const int LP = L * P;
     const T *vbase = value + ((long long)b * S * M + m) * 32 + sub * VEC;
-    const float2 *locp = reinterpret_cast<const float2 *>(loc) + row * L * P;
-    const float *attp = attn + row * L * P;
+    const float2 *locp = reinterpret_cast<const float2 *>(loc) + row * LP;
+    const float *attp = attn + row * LP;
 
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
-    for (int l = 0; l < L; ++l) {
-        const int H = s_h[l], W = s_w[l];
-        const T *vl = vbase + (long long)s_start[l] * pix;
-#pragma unroll 4
-        for (int p = 0; p < P; ++p) {
-            const float2 xy = __ldg(locp + l * P + p);
-            const float a = __ldg(attp + l * P + p);
-            const Corner c = make_corner(xy.x, xy.y, H, W, pix);
-            float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
-            Row<T>::load(vl + c.off00, v00);
-            Row<T>::load(vl + c.off01, v01);
-            Row<T>::load(vl + c.off10, v10);
-            Row<T>::load(vl + c.off11, v11);
-            const float w00 = c.w00 * a, w01 = c.w01 * a, w10 = c.w10 * a, w11 = c.w11 * a;
+    for (int s0 = 0; s0 < LP; s0 += LANES) {
+        // ---- produce: this lane prepares sample s0 + sub of its row
+        const int sm = s0 + sub;
+        int enc = 0;                              // element offset of the top-left corner | dx | dy<<1
+        float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+        bool valid = false;
+        if (sm < LP && live) {
+            const int l = level_of(sm, magic);
+            const float2 xy = __ldg(locp + sm);
+            const float a = __ldg(attp + sm);
+            const Corner c = make_corner(xy.x, xy.y, s_h[l], s_w[l]);
+            enc = (c.pidx * pix) | c.dx | (c.dy << 1);
+            valid = c.valid;
+            w00 = c.w00 * a; w01 = c.w01 * a; w10 = c.w10 * a; w11 = c.w11 * a;
+        }
+        uint32_t wa = 0, wb = 0;
+        if constexpr (kHalf) { wa = pack_bf16x2(w00, w01); wb = pack_bf16x2(w10, w11); }
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        // ---- consume: every lane of the group walks the LANES samples of this round
 #pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                acc[i] += w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
+        for (int j = 0; j < LANES; ++j) {
+            if (s0 + j >= LP) break;                                   // warp-uniform
+            if (!(vm & (GroupMask<LANES>::kBits << j))) continue;      // nobody needs it (uniform)
+            const int src = grp * LANES + j;
+            const int e = __shfl_sync(0xffffffffu, enc, src);
+            const int l = level_of(s0 + j, magic);
+            const int rs = s_w[l] * pix;
+            const T *p00 = vbase + (long long)s_start[l] * pix + (e & ~3);
+            const int ox = (e & 1) ? pix : 0, oy = (e & 2) ? rs : 0;
+            Vec<T> v00, v01, v10, v11;
+            v00.load(p00); v01.load(p00 + ox); v10.load(p00 + oy); v11.load(p00 + oy + ox);
+            if constexpr (kHalf) {
+                const uint32_t qa = __shfl_sync(0xffffffffu, wa, src);
+                const uint32_t qb = __shfl_sync(0xffffffffu, wb, src);
+                unsigned short h00, h01, h10, h11;
+                split16(qa, h00, h01);
+                split16(qb, h10, h11);
+                v00.axpy_h(h00, acc); v01.axpy_h(h01, acc); v10.axpy_h(h10, acc); v11.axpy_h(h11, acc);
+            } else {
+                const float q00 = __shfl_sync(0xffffffffu, w00, src);
+                const float q01 = __shfl_sync(0xffffffffu, w01, src);
+                const float q10 = __shfl_sync(0xffffffffu, w10, src);
+                const float q11 = __shfl_sync(0xffffffffu, w11, src);
+                v00.axpy(q00, acc); v01.axpy(q01, acc); v10.axpy(q10, acc); v11.axpy(q11, acc);
+            }
         }
     }
-    store_vec<TO, VEC>(out + row * 32 + sub * VEC, acc);
+    if (live) store_vec<TO, VEC>(out + row * 32 + sub * VEC, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,77 +243,115 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const int64_t *__restrict__ level_start, const float *__restrict__ loc,
              const float *__restrict__ attn, const TG *__restrict__ grad_out,
              float *__restrict__ grad_value, float *__restrict__ grad_loc,
-             float *__restrict__ grad_attn, int S, int M, int Q, int L, int P, long long rows) {
-    constexpr int VEC = Row<T>::kVec, LANES = 32 / VEC, G = 32 / LANES;
+             float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M, int Q,
+             int L, int P, int magic, long long rows) {
+    constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
+    constexpr bool kHalfDot = (VEC == 8) && (sizeof(TG) == 2);
     __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
     load_levels(level_hw, level_start, L, s_h, s_w, s_start);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
     long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * G + grp;
-    const bool live = row < rows;          // dead groups still take part in the shuffles
+    const bool live = row < rows;
     if (!live) row = rows - 1;
     const int m = (int)(row % M);
-    const int b = (int)(row / ((long long)M * Q));
+    const int b = value_map_of(row_map, row, M, Q);
     const int pix = M * 32;
+    const int LP = L * P;
     const long long voff = ((long long)b * S * M + m) * 32 + sub * VEC;
-    const float2 *locp = reinterpret_cast<const float2 *>(loc) + row * L * P;
-    const float *attp = attn + row * L * P;
+    const float2 *locp = reinterpret_cast<const float2 *>(loc) + row * LP;
+    const float *attp = attn + row * LP;
 
-    float g[VEC];   // grad_out row, in the gradient's own storage type
+    float g[VEC];                                 // this lane's slice of the grad_out row, fp32
     load_vec<TG, VEC>(grad_out + row * 32 + sub * VEC, g);
+    uint4 gh = make_uint4(0, 0, 0, 0);            // the same slice as packed bf16, for FHFMA dots
+    if constexpr (kHalfDot)
+        gh = __ldg(reinterpret_cast<const uint4 *>(grad_out + row * 32 + sub * VEC));
 
-    for (int l = 0; l < L; ++l) {
-        const int H = s_h[l], W = s_w[l];
-        const long long lbase = voff + (long long)s_start[l] * pix;
-        const T *vl = value + lbase;
-        float *gvl = grad_value + lbase;
-#pragma unroll 2
-        for (int p = 0; p < P; ++p) {
-            const long long si = row * L * P + l * P + p;
-            const float2 xy = __ldg(locp + l * P + p);
-            const float a = __ldg(attp + l * P + p);
-            const Corner c = make_corner(xy.x, xy.y, H, W, pix);
-            float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
-            Row<T>::load(vl + c.off00, v00);
-            Row<T>::load(vl + c.off01, v01);
-            Row<T>::load(vl + c.off10, v10);
-            Row<T>::load(vl + c.off11, v11);
-            const float hx = 1.f - c.lx, hy = 1.f - c.ly;
-            float ga = 0.f, gx = 0.f, gy = 0.f;
-            float t00[VEC], t01[VEC], t10[VEC], t11[VEC];
+    for (int s0 = 0; s0 < LP; s0 += LANES) {
+        // ---- produce
+        const int sm = s0 + sub;
+        Corner c;
+        c.pidx = 0; c.dx = c.dy = 0; c.w00 = c.w01 = c.w10 = c.w11 = 0.f; c.lx = c.ly = 0.f;
+        c.f00 = c.f01 = c.f10 = c.f11 = 0.f; c.valid = false;
+        float a = 0.f;
+        int Hm = 1, Wm = 1;
+        const bool mine = sm < LP && live;
+        if (mine) {
+            const int l = level_of(sm, magic);
+            Hm = s_h[l]; Wm = s_w[l];
+            const float2 xy = __ldg(locp + sm);
+            a = __ldg(attp + sm);
+            c = make_corner(xy.x, xy.y, Hm, Wm);
+        }
+        const int enc = (c.pidx * pix) | c.dx | (c.dy << 1);
+        const float wa00 = c.w00 * a, wa01 = c.w01 * a, wa10 = c.w10 * a, wa11 = c.w11 * a;
+        const unsigned vm = __ballot_sync(0xffffffffu, c.valid);
+        // d[j][k]: this lane's partial <grad_out, corner k> for sample j of the round
+        float d[LANES][4];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float t = g[i] * a;
-                t00[i] = c.w00 * t; t01[i] = c.w01 * t; t10[i] = c.w10 * t; t11[i] = c.w11 * t;
-                // corners outside the map read as zero, whatever their (clamped) address holds
-                const float a00 = c.f00 * v00[i], a01 = c.f01 * v01[i], a10 = c.f10 * v10[i],
-                            a11 = c.f11 * v11[i];
-                ga += g[i] * (hy * (hx * a00 + c.lx * a01) + c.ly * (hx * a10 + c.lx * a11));
-                gx += t * (hy * (a01 - a00) + c.ly * (a11 - a10));
-                gy += t * (hx * (a10 - a00) + c.lx * (a11 - a01));
+        for (int j = 0; j < LANES; ++j) { d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f; }
+        // ---- consume
+#pragma unroll
+        for (int j = 0; j < LANES; ++j) {
+            if (s0 + j >= LP) break;
+            if (!(vm & (GroupMask<LANES>::kBits << j))) continue;
+            const int src = grp * LANES + j;
+            const int e = __shfl_sync(0xffffffffu, enc, src);
+            const float q00 = __shfl_sync(0xffffffffu, wa00, src);
+            const float q01 = __shfl_sync(0xffffffffu, wa01, src);
+            const float q10 = __shfl_sync(0xffffffffu, wa10, src);
+            const float q11 = __shfl_sync(0xffffffffu, wa11, src);
+            const int l = level_of(s0 + j, magic);
+            const int rs = s_w[l] * pix;
+            const long long o00 = voff + (long long)s_start[l] * pix + (e & ~3);
+            const int ox = (e & 1) ? pix : 0, oy = (e & 2) ? rs : 0;
+            Vec<T> v00, v01, v10, v11;
+            v00.load(value + o00); v01.load(value + o00 + ox);
+            v10.load(value + o00 + oy); v11.load(value + o00 + oy + ox);
+            if constexpr (kHalfDot) {
+                d[j][0] = v00.dot_h(gh); d[j][1] = v01.dot_h(gh);
+                d[j][2] = v10.dot_h(gh); d[j][3] = v11.dot_h(gh);
+            } else {
+                d[j][0] = v00.dot(g); d[j][1] = v01.dot(g); d[j][2] = v10.dot(g); d[j][3] = v11.dot(g);
             }
-            // scatter: 16 B vector reductions, skipped entirely for zero-weight corners
-            if (live) {
+            // scatter w * a * g with 16 B reductions; zero-weight corners are skipped
+            float *gv = grad_value + o00;
 #pragma unroll
-                for (int i = 0; i < VEC; i += 4) {
-                    if (c.w00 != 0.f) red_add_v4(gvl + c.off00 + i, t00[i], t00[i + 1], t00[i + 2], t00[i + 3]);
-                    if (c.w01 != 0.f) red_add_v4(gvl + c.off01 + i, t01[i], t01[i + 1], t01[i + 2], t01[i + 3]);
-                    if (c.w10 != 0.f) red_add_v4(gvl + c.off10 + i, t10[i], t10[i + 1], t10[i + 2], t10[i + 3]);
-                    if (c.w11 != 0.f) red_add_v4(gvl + c.off11 + i, t11[i], t11[i + 1], t11[i + 2], t11[i + 3]);
+            for (int i = 0; i < VEC; i += 4) {
+                if (q00 != 0.f) red_add_v4(gv + i, q00 * g[i], q00 * g[i + 1], q00 * g[i + 2], q00 * g[i + 3]);
+                if (q01 != 0.f) red_add_v4(gv + ox + i, q01 * g[i], q01 * g[i + 1], q01 * g[i + 2], q01 * g[i + 3]);
+                if (q10 != 0.f) red_add_v4(gv + oy + i, q10 * g[i], q10 * g[i + 1], q10 * g[i + 2], q10 * g[i + 3]);
+                if (q11 != 0.f) red_add_v4(gv + oy + ox + i, q11 * g[i], q11 * g[i + 1], q11 * g[i + 2], q11 * g[i + 3]);
+            }
+        }
+        // ---- reduce-scatter the dots over the group: lane `sub` ends with the totals of sample
+        //      s0 + sub (the one whose scalars it holds).  log2(LANES) halving steps.
+#pragma unroll
+        for (int step = LANES / 2; step > 0; step >>= 1) {
+            const bool upper = (sub & step) != 0;
+#pragma unroll
+            for (int j = 0; j < step; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // keep the half of the samples whose index has this bit equal to mine
+                    const float keep = upper ? d[j + step][k] : d[j][k];
+                    const float send = upper ? d[j][k] : d[j + step][k];
+                    d[j][k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
                 }
             }
-            // reduce the three scalars over the lanes that share this row
-#pragma unroll
-            for (int s = LANES / 2; s > 0; s >>= 1) {
-                ga += __shfl_xor_sync(0xffffffffu, ga, s);
-                gx += __shfl_xor_sync(0xffffffffu, gx, s);
-                gy += __shfl_xor_sync(0xffffffffu, gy, s);
-            }
-            if (live && sub == 0) {
-                grad_attn[si] = ga;
-                reinterpret_cast<float2 *>(grad_loc)[si] = make_float2((float)W * gx, (float)H * gy);
-            }
+        }
+        if (mine) {
+            const float hx = 1.f - c.lx, hy = 1.f - c.ly;
+            const float d00 = c.f00 * d[0][0], d01 = c.f01 * d[0][1], d10 = c.f10 * d[0][2],
+                        d11 = c.f11 * d[0][3];
+            const float ga = hy * (hx * d00 + c.lx * d01) + c.ly * (hx * d10 + c.lx * d11);
+            const float gx = a * (hy * (d01 - d00) + c.ly * (d11 - d10));
+            const float gy = a * (hx * (d10 - d00) + c.lx * (d11 - d01));
+            const long long si = row * LP + sm;
+            grad_attn[si] = ga;
+            reinterpret_cast<float2 *>(grad_loc)[si] = make_float2((float)Wm * gx, (float)Hm * gy);
         }
     }
 }
@@ -204,16 +363,17 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
                  const int64_t *__restrict__ level_start, const float *__restrict__ loc,
-                 const float *__restrict__ attn, TO *__restrict__ out, int S, int M, int D, int Q,
-                 int L, int P, long long rows) {
+                 const float *__restrict__ attn, TO *__restrict__ out,
+                 const int *__restrict__ row_map, int S, int M, int D, int Q, int L, int P,
+                 long long rows) {
     __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
     load_levels(level_hw, level_start, L, s_h, s_w, s_start);
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int m = (int)(row % M);
-    const int b = (int)(row / ((long long)M * Q));
-    const int pix = M * D;
+    const int b = value_map_of(row_map, row, M, Q);
+    const long long pix = (long long)M * D;
     for (int c0 = lane; c0 < D; c0 += 32) {
         float acc = 0.f;
         for (int l = 0; l < L; ++l) {
@@ -221,10 +381,12 @@ msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_
             const T *vl = value + ((long long)b * S + s_start[l]) * pix + (long long)m * D + c0;
             for (int p = 0; p < P; ++p) {
                 const long long si = row * L * P + l * P + p;
-                const Corner c = make_corner(loc[2 * si], loc[2 * si + 1], H, W, pix);
+                const Corner c = make_corner(loc[2 * si], loc[2 * si + 1], H, W);
                 const float a = attn[si];
-                acc += a * (c.w00 * Row<T>::load1(vl + c.off00) + c.w01 * Row<T>::load1(vl + c.off01) +
-                            c.w10 * Row<T>::load1(vl + c.off10) + c.w11 * Row<T>::load1(vl + c.off11));
+                const T *p00 = vl + c.pidx * pix;
+                const long long ox = c.dx ? pix : 0, oy = c.dy ? W * pix : 0;
+                acc += a * (c.w00 * Row<T>::load1(p00) + c.w01 * Row<T>::load1(p00 + ox) +
+                            c.w10 * Row<T>::load1(p00 + oy) + c.w11 * Row<T>::load1(p00 + oy + ox));
             }
         }
         Row<TO>::store1(out + row * D + c0, acc);
@@ -237,37 +399,38 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_
                  const int64_t *__restrict__ level_start, const float *__restrict__ loc,
                  const float *__restrict__ attn, const TG *__restrict__ grad_out,
                  float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                 float *__restrict__ grad_attn, int S, int M, int D, int Q, int L, int P,
-                 long long rows) {
+                 float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M,
+                 int D, int Q, int L, int P, long long rows) {
     __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
     load_levels(level_hw, level_start, L, s_h, s_w, s_start);
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     if (row >= rows) return;   // whole warp leaves together
     const int m = (int)(row % M);
-    const int b = (int)(row / ((long long)M * Q));
-    const int pix = M * D;
+    const int b = value_map_of(row_map, row, M, Q);
+    const long long pix = (long long)M * D;
     for (int l = 0; l < L; ++l) {
         const int H = s_h[l], W = s_w[l];
         const long long lbase = ((long long)b * S + s_start[l]) * pix + (long long)m * D;
         for (int p = 0; p < P; ++p) {
             const long long si = row * L * P + l * P + p;
-            const float lxn = loc[2 * si], lyn = loc[2 * si + 1];
-            const Corner c = make_corner(lxn, lyn, H, W, pix);
+            const Corner c = make_corner(loc[2 * si], loc[2 * si + 1], H, W);
+            const long long i00 = lbase + c.pidx * pix;
+            const long long ox = c.dx ? pix : 0, oy = c.dy ? W * pix : 0;
+            const long long i01 = i00 + ox, i10 = i00 + oy, i11 = i00 + oy + ox;
             const float a = attn[si];
             const float hx = 1.f - c.lx, hy = 1.f - c.ly;
-            const float f00 = c.f00, f01 = c.f01, f10 = c.f10, f11 = c.f11;
             float ga = 0.f, gx = 0.f, gy = 0.f;
             for (int c0 = lane; c0 < D; c0 += 32) {
                 const float gc = Row<TG>::load1(grad_out + row * D + c0), t = gc * a;
-                const float v00 = f00 * Row<T>::load1(value + lbase + c.off00 + c0);
-                const float v01 = f01 * Row<T>::load1(value + lbase + c.off01 + c0);
-                const float v10 = f10 * Row<T>::load1(value + lbase + c.off10 + c0);
-                const float v11 = f11 * Row<T>::load1(value + lbase + c.off11 + c0);
-                if (c.w00 != 0.f) atomicAdd(grad_value + lbase + c.off00 + c0, c.w00 * t);
-                if (c.w01 != 0.f) atomicAdd(grad_value + lbase + c.off01 + c0, c.w01 * t);
-                if (c.w10 != 0.f) atomicAdd(grad_value + lbase + c.off10 + c0, c.w10 * t);
-                if (c.w11 != 0.f) atomicAdd(grad_value + lbase + c.off11 + c0, c.w11 * t);
+                const float v00 = c.f00 * Row<T>::load1(value + i00 + c0);
+                const float v01 = c.f01 * Row<T>::load1(value + i01 + c0);
+                const float v10 = c.f10 * Row<T>::load1(value + i10 + c0);
+                const float v11 = c.f11 * Row<T>::load1(value + i11 + c0);
+                if (c.w00 != 0.f) atomicAdd(grad_value + i00 + c0, c.w00 * t);
+                if (c.w01 != 0.f) atomicAdd(grad_value + i01 + c0, c.w01 * t);
+                if (c.w10 != 0.f) atomicAdd(grad_value + i10 + c0, c.w10 * t);
+                if (c.w11 != 0.f) atomicAdd(grad_value + i11 + c0, c.w11 * t);
                 ga += gc * (hy * (hx * v00 + c.lx * v01) + c.ly * (hx * v10 + c.lx * v11));
                 gx += t * (hy * (v01 - v00) + c.ly * (v11 - v10));
                 gy += t * (hx * (v10 - v00) + c.lx * (v11 - v01));
@@ -296,44 +459,93 @@ static int check_dims(const char *who, int B, int S, int M, int D, int Q, int L,
     if (L > kMaxLevels) return fail("%s: at most 16 levels are supported (got %lld)", who, L);
     if ((long long)S * M * D >= (1ll << 31))
         return fail("%s: one batch item of value exceeds 2^31 elements", who);
+    if ((long long)L * P * P >= 65536) return fail("%s: num_levels * num_points^2 must be < 65536", who);
     return 0;
 }
 
 template <typename T, typename TO>
-static int launch_fwd(const void *value, const int64_t *hw, const int64_t *ls, const float *loc,
-                      const float *attn, void *out, int S, int M, int D, int Q, int L, int P,
-                      long long rows, cudaStream_t st) {
+static int launch_fwd(const char *who, const void *value, const int64_t *hw, const int64_t *ls,
+                      const float *loc, const float *attn, void *out, const int *row_map, int S,
+                      int M, int D, int Q, int L, int P, long long rows, cudaStream_t st) {
     if (D == 32) {
-        constexpr int G = 32 / (32 / Row<T>::kVec);
+        constexpr int G = Vec<T>::N;      // rows per warp == channels per lane (4 or 8)
         const long long per_block = (long long)(kThreads / 32) * G;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
         msda_fwd_d32<T, TO><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn, (TO *)out,
-                                                       S, M, Q, L, P, rows);
+                                                       row_map, S, M, Q, L, P, (65536 + P - 1) / P, rows);
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
         msda_fwd_generic<T, TO><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
-                                                           (TO *)out, S, M, D, Q, L, P, rows);
+                                                           (TO *)out, row_map, S, M, D, Q, L, P, rows);
     }
-    return check_launch("bevf_msda_forward");
+    return check_launch(who);
 }
 
 template <typename T, typename TG>
-static int launch_bwd(const void *value, const int64_t *hw, const int64_t *ls, const float *loc,
-                      const float *attn, const void *go, float *gv, float *gl, float *ga, int S,
-                      int M, int D, int Q, int L, int P, long long rows, cudaStream_t st) {
+static int launch_bwd(const char *who, const void *value, const int64_t *hw, const int64_t *ls,
+                      const float *loc, const float *attn, const void *go, float *gv, float *gl,
+                      float *ga, const int *row_map, int S, int M, int D, int Q, int L, int P,
+                      long long rows, cudaStream_t st) {
     if (D == 32) {
-        constexpr int G = 32 / (32 / Row<T>::kVec);
+        constexpr int G = Vec<T>::N;
         const long long per_block = (long long)(kThreads / 32) * G;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
         msda_bwd_d32<T, TG><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
-                                                       (const TG *)go, gv, gl, ga, S, M, Q, L, P, rows);
+                                                       (const TG *)go, gv, gl, ga, row_map, S, M, Q,
+                                                       L, P, (65536 + P - 1) / P, rows);
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
         msda_bwd_generic<T, TG><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
-                                                           (const TG *)go, gv, gl, ga, S, M, D, Q, L,
-                                                           P, rows);
+                                                           (const TG *)go, gv, gl, ga, row_map, S, M,
+                                                           D, Q, L, P, rows);
     }
-    return check_launch("bevf_msda_backward");
+    return check_launch(who);
+}
+
+static int msda_forward_impl(const char *who, const void *value, int value_dtype,
+                             const int64_t *level_hw, const int64_t *level_start, const float *loc,
+                             const float *attn, void *out, int out_dtype, const int *row_map, int B,
+                             int S, int M, int D, int Q, int L, int P, void *stream) {
+    if (int e = check_dims(who, B, S, M, D, Q, L, P)) return e;
+    const long long rows = (row_map ? 1ll : (long long)B) * Q * M;
+    if (rows == 0) return 0;
+    if (!value || !level_hw || !level_start || !loc || !attn || !out)
+        return fail("%s: null pointer argument", who);
+    if (!aligned16(value) || !aligned16(loc) || !aligned16(attn) || !aligned16(out))
+        return fail("%s: device pointers must be 16-byte aligned", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vb = value_dtype == BEVF_DTYPE_BF16, ob = out_dtype == BEVF_DTYPE_BF16;
+    if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (out_dtype != BEVF_DTYPE_F32 && !ob))
+        return fail("%s: unsupported dtype code", who);
+    if (!vb && !ob) return launch_fwd<float, float>(who, value, level_hw, level_start, loc, attn, out, row_map, S, M, D, Q, L, P, rows, st);
+    if (vb && ob) return launch_fwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, out, row_map, S, M, D, Q, L, P, rows, st);
+    if (vb && !ob) return launch_fwd<bf16, float>(who, value, level_hw, level_start, loc, attn, out, row_map, S, M, D, Q, L, P, rows, st);
+    return fail("%s: fp32 value with bf16 output is not supported", who);
+}
+
+static int msda_backward_impl(const char *who, const void *value, int value_dtype,
+                              const int64_t *level_hw, const int64_t *level_start, const float *loc,
+                              const float *attn, const void *grad_out, int grad_out_dtype,
+                              float *grad_value, float *grad_loc, float *grad_attn,
+                              const int *row_map, int B, int S, int M, int D, int Q, int L, int P,
+                              void *stream) {
+    if (int e = check_dims(who, B, S, M, D, Q, L, P)) return e;
+    const long long rows = (row_map ? 1ll : (long long)B) * Q * M;
+    if (rows == 0) return 0;
+    if (!value || !level_hw || !level_start || !loc || !attn || !grad_out || !grad_value ||
+        !grad_loc || !grad_attn)
+        return fail("%s: null pointer argument", who);
+    if (!aligned16(value) || !aligned16(loc) || !aligned16(attn) || !aligned16(grad_out) ||
+        !aligned16(grad_value) || !aligned16(grad_loc) || !aligned16(grad_attn))
+        return fail("%s: device pointers must be 16-byte aligned", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vb = value_dtype == BEVF_DTYPE_BF16, gb = grad_out_dtype == BEVF_DTYPE_BF16;
+    if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (grad_out_dtype != BEVF_DTYPE_F32 && !gb))
+        return fail("%s: unsupported dtype code", who);
+    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, S, M, D, Q, L, P, rows, st);
+    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, S, M, D, Q, L, P, rows, st);
+    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, S, M, D, Q, L, P, rows, st);
+    return fail("%s: fp32 value with bf16 grad_out is not supported", who);
 }
 
 }  // namespace bevf
@@ -344,21 +556,8 @@ extern "C" int bevf_msda_forward(const void *value, int value_dtype, const int64
                                  const int64_t *level_start, const float *loc, const float *attn,
                                  void *out, int out_dtype, int B, int S, int M, int D, int Q, int L,
                                  int P, void *stream) {
-    if (int e = check_dims("bevf_msda_forward", B, S, M, D, Q, L, P)) return e;
-    if (!value || !level_hw || !level_start || !loc || !attn || !out)
-        return fail("%s: null pointer argument", "bevf_msda_forward");
-    if (!aligned16(value) || !aligned16(loc) || !aligned16(attn) || !aligned16(out))
-        return fail("%s: device pointers must be 16-byte aligned", "bevf_msda_forward");
-    const long long rows = (long long)B * Q * M;
-    if (rows == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool vb = value_dtype == BEVF_DTYPE_BF16, ob = out_dtype == BEVF_DTYPE_BF16;
-    if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (out_dtype != BEVF_DTYPE_F32 && !ob))
-        return fail("%s: unsupported dtype code", "bevf_msda_forward");
-    if (!vb && !ob) return launch_fwd<float, float>(value, level_hw, level_start, loc, attn, out, S, M, D, Q, L, P, rows, st);
-    if (vb && ob) return launch_fwd<bf16, bf16>(value, level_hw, level_start, loc, attn, out, S, M, D, Q, L, P, rows, st);
-    if (vb && !ob) return launch_fwd<bf16, float>(value, level_hw, level_start, loc, attn, out, S, M, D, Q, L, P, rows, st);
-    return fail("%s: fp32 value with bf16 output is not supported", "bevf_msda_forward");
+    return msda_forward_impl("bevf_msda_forward", value, value_dtype, level_hw, level_start, loc,
+                             attn, out, out_dtype, nullptr, B, S, M, D, Q, L, P, stream);
 }
 
 extern "C" int bevf_msda_backward(const void *value, int value_dtype, const int64_t *level_hw,
@@ -366,21 +565,29 @@ extern "C" int bevf_msda_backward(const void *value, int value_dtype, const int6
                                   const void *grad_out, int grad_out_dtype, float *grad_value,
                                   float *grad_loc, float *grad_attn, int B, int S, int M, int D,
                                   int Q, int L, int P, void *stream) {
-    if (int e = check_dims("bevf_msda_backward", B, S, M, D, Q, L, P)) return e;
-    if (!value || !level_hw || !level_start || !loc || !attn || !grad_out || !grad_value ||
-        !grad_loc || !grad_attn)
-        return fail("%s: null pointer argument", "bevf_msda_backward");
-    if (!aligned16(value) || !aligned16(loc) || !aligned16(attn) || !aligned16(grad_out) ||
-        !aligned16(grad_value) || !aligned16(grad_loc) || !aligned16(grad_attn))
-        return fail("%s: device pointers must be 16-byte aligned", "bevf_msda_backward");
-    const long long rows = (long long)B * Q * M;
-    if (rows == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool vb = value_dtype == BEVF_DTYPE_BF16, gb = grad_out_dtype == BEVF_DTYPE_BF16;
-    if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (grad_out_dtype != BEVF_DTYPE_F32 && !gb))
-        return fail("%s: unsupported dtype code", "bevf_msda_backward");
-    if (!vb && !gb) return launch_bwd<float, float>(value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, S, M, D, Q, L, P, rows, st);
-    if (vb && gb) return launch_bwd<bf16, bf16>(value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, S, M, D, Q, L, P, rows, st);
-    if (vb && !gb) return launch_bwd<bf16, float>(value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, S, M, D, Q, L, P, rows, st);
-    return fail("%s: fp32 value with bf16 grad_out is not supported", "bevf_msda_backward");
+    return msda_backward_impl("bevf_msda_backward", value, value_dtype, level_hw, level_start, loc,
+                              attn, grad_out, grad_out_dtype, grad_value, grad_loc, grad_attn,
+                              nullptr, B, S, M, D, Q, L, P, stream);
+}
+
+extern "C" int bevf_msda_rows_forward(const void *value, int value_dtype, const int64_t *level_hw,
+                                      const int64_t *level_start, const float *loc,
+                                      const float *attn, void *out, int out_dtype,
+                                      const int32_t *row_map, int B, int S, int M, int D, int R,
+                                      int L, int P, void *stream) {
+    if (!row_map && R > 0) return fail("%s: row_map is null", "bevf_msda_rows_forward");
+    return msda_forward_impl("bevf_msda_rows_forward", value, value_dtype, level_hw, level_start,
+                             loc, attn, out, out_dtype, row_map, B, S, M, D, R, L, P, stream);
+}
+
+extern "C" int bevf_msda_rows_backward(const void *value, int value_dtype, const int64_t *level_hw,
+                                       const int64_t *level_start, const float *loc,
+                                       const float *attn, const void *grad_out, int grad_out_dtype,
+                                       float *grad_value, float *grad_loc, float *grad_attn,
+                                       const int32_t *row_map, int B, int S, int M, int D, int R,
+                                       int L, int P, void *stream) {
+    if (!row_map && R > 0) return fail("%s: row_map is null", "bevf_msda_rows_backward");
+    return msda_backward_impl("bevf_msda_rows_backward", value, value_dtype, level_hw, level_start,
+                              loc, attn, grad_out, grad_out_dtype, grad_value, grad_loc, grad_attn,
+                              row_map, B, S, M, D, R, L, P, stream);
 }

@@ -1,0 +1,400 @@
+"""BEVFormerEncoder / BEVFormerLayer / MyCustomBaseTransformerLayer / FFN on the B200 kernels.
+
+Drop-ins for projects/mmdet3d_plugin/bevformer/modules/encoder.py:24-406 and
+custom_base_transformer_layer.py:37-260, plus the two mmcv classes those files instantiate from the
+config (``FFN`` and ``TransformerLayerSequence``; mmcv-full==1.4.0 semantics as in SURVEY.md
+Appendix B).  Parameter names follow the reference ``state_dict``:
+``layers.{i}.attentions.{0,1}.*``, ``layers.{i}.ffns.0.layers.0.0.*``, ``layers.{i}.ffns.0.layers.1.*``,
+``layers.{i}.norms.{0,1,2}.*``.
+
+Per layer the reference issues ~60 launches (GEMMs, element-wise ops, copies, the op); here a layer
+is: one stacked offsets|logits projection + value/output projections per attention, one prep
+kernel, one sampler launch, one combine (SCA), and a fused dropout-residual-LayerNorm kernel after
+each of the three blocks.
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .linear import linear
+from .registry import (FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, _register,
+                       build_attention, build_feedforward_network, build_transformer_layer)
+from .spatial_cross_attention import ScaPlan, SpatialCrossAttention
+from .temporal_self_attention import TemporalSelfAttention
+
+_OPS = ("self_attn", "norm", "ffn", "cross_attn")
+
+
+class FFN(nn.Module):
+    """mmcv's FFN: ``identity + Dropout(Linear(Dropout(act(Linear(x)))))`` with the module tree
+    ``layers = Sequential(Sequential(Linear, act, Dropout), ..., Linear, Dropout)`` so that the
+    checkpoint keys ``layers.0.0.*`` / ``layers.1.*`` line up."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                 act_cfg=dict(type="ReLU", inplace=True), ffn_drop=0.0, dropout_layer=None,
+                 add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        if num_fcs < 2:
+            raise AssertionError(f"num_fcs should be no less than 2. got {num_fcs}.")
+        act = (act_cfg or {}).get("type", "ReLU")
+        if act not in ("ReLU", "GELU"):
+            raise KeyError(f"unsupported FFN activation {act}")
+        self.embed_dims, self.feedforward_channels, self.num_fcs = embed_dims, feedforward_channels, num_fcs
+        self.act_type = act
+        blocks, width = [], embed_dims
+        for _ in range(num_fcs - 1):
+            blocks.append(nn.Sequential(nn.Linear(width, feedforward_channels),
+                                        nn.ReLU(inplace=True) if act == "ReLU" else nn.GELU(),
+                                        nn.Dropout(ffn_drop)))
+            width = feedforward_channels
+        blocks += [nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop)]
+        self.layers = nn.Sequential(*blocks)
+        self.dropout_layer = nn.Identity()
+        self.add_identity = add_identity
+
+    def transform(self, x):
+        """The stack without the identity add (hidden dropout included, final dropout not)."""
+        h = x
+        for blk in list(self.layers)[: self.num_fcs - 1]:
+            h = linear(h, blk[0].weight, blk[0].bias, relu=self.act_type == "ReLU")
+            if self.act_type != "ReLU":
+                h = blk[1](h)
+            h = blk[2](h)
+        last = self.layers[self.num_fcs - 1]
+        return linear(h, last.weight, last.bias)
+
+    def forward(self, x, identity=None):
+        out = self.layers[self.num_fcs](self.transform(x))
+        if not self.add_identity:
+            return self.dropout_layer(out)
+        return (x if identity is None else identity) + self.dropout_layer(out)
+
+
+_register(FEEDFORWARD_NETWORK, FFN, name="FFN")
+
+
+def _fused_norm(norm: nn.LayerNorm, x, residual):
+    """LayerNorm(x + residual) in one kernel (fp32 statistics)."""
+    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps)
+
+
+class MyCustomBaseTransformerLayer(nn.Module):
+    """Builds ``attentions`` / ``ffns`` / ``norms`` from config dicts and runs them in
+    ``operation_order`` (custom_base_transformer_layer.py:72-260)."""
+
+    def __init__(self, attn_cfgs=None, ffn_cfgs=None, operation_order=None,
+                 norm_cfg=dict(type="LN"), init_cfg=None, batch_first=True, **kwargs):
+        super().__init__()
+        ffn_cfgs = dict(type="FFN", embed_dims=256, feedforward_channels=1024, num_fcs=2, ffn_drop=0.0,
+                        act_cfg=dict(type="ReLU", inplace=True)) if ffn_cfgs is None else copy.deepcopy(ffn_cfgs)
+        legacy = dict(feedforward_channels="feedforward_channels", ffn_dropout="ffn_drop",
+                      ffn_num_fcs="num_fcs")
+        for old, new in legacy.items():                       # deprecated kwargs the configs still use
+            if old in kwargs:
+                ffn_cfgs[new] = kwargs[old]
+        if "act_cfg" in kwargs and isinstance(ffn_cfgs, dict):
+            ffn_cfgs.setdefault("act_cfg", kwargs["act_cfg"])
+        operation_order = tuple(operation_order)
+        if not set(operation_order) <= set(_OPS):
+            raise AssertionError(f"operation_order of {type(self).__name__} may only contain {_OPS}")
+        self.init_cfg = init_cfg
+        self.batch_first = batch_first
+        self.operation_order = operation_order
+        self.norm_cfg = norm_cfg
+        self.pre_norm = operation_order[0] == "norm"
+        self.num_attn = operation_order.count("self_attn") + operation_order.count("cross_attn")
+        if isinstance(attn_cfgs, dict):
+            attn_cfgs = [copy.deepcopy(attn_cfgs) for _ in range(self.num_attn)]
+        else:
+            attn_cfgs = [copy.deepcopy(c) for c in attn_cfgs]
+            if len(attn_cfgs) != self.num_attn:
+                raise AssertionError(f"{len(attn_cfgs)} attention configs for {self.num_attn} attention "
+                                     f"operations in {operation_order}")
+        self.attentions = nn.ModuleList()
+        names = [n for n in operation_order if n in ("self_attn", "cross_attn")]
+        for cfg, name in zip(attn_cfgs, names):
+            if "batch_first" in cfg:
+                assert self.batch_first == cfg["batch_first"]
+            else:
+                cfg["batch_first"] = self.batch_first
+            att = build_attention(cfg)
+            att.operation_name = name
+            self.attentions.append(att)
+        self.embed_dims = self.attentions[0].embed_dims
+
+        n_ffn = operation_order.count("ffn")
+        if isinstance(ffn_cfgs, dict):
+            ffn_cfgs = [copy.deepcopy(ffn_cfgs) for _ in range(n_ffn)]
+        assert len(ffn_cfgs) == n_ffn
+        self.ffns = nn.ModuleList()
+        for cfg in ffn_cfgs:
+            cfg = dict(cfg)
+            cfg.setdefault("embed_dims", self.embed_dims)
+            assert cfg["embed_dims"] == self.embed_dims
+            self.ffns.append(build_feedforward_network(cfg))
+
+        if (norm_cfg or {}).get("type", "LN") != "LN":
+            raise KeyError("only LayerNorm ('LN') is supported")
+        self.norms = nn.ModuleList(
+            nn.LayerNorm(self.embed_dims, eps=(norm_cfg or {}).get("eps", 1e-5))
+            for _ in range(operation_order.count("norm")))
+
+    def _attn_masks(self, attn_masks):
+        if attn_masks is None:
+            return [None] * self.num_attn
+        if isinstance(attn_masks, torch.Tensor):
+            warnings.warn(f"Use same attn_mask in all attentions in {type(self).__name__} ")
+            return [copy.deepcopy(attn_masks) for _ in range(self.num_attn)]
+        assert len(attn_masks) == self.num_attn
+        return attn_masks
+
+    def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        masks = self._attn_masks(attn_masks)
+        ni = ai = fi = 0
+        identity = query
+        for op in self.operation_order:
+            if op == "self_attn":
+                query = self.attentions[ai](query, query, query, identity if self.pre_norm else None,
+                                            query_pos=query_pos, key_pos=query_pos,
+                                            attn_mask=masks[ai],
+                                            key_padding_mask=query_key_padding_mask, **kwargs)
+                ai += 1
+                identity = query
+            elif op == "cross_attn":
+                query = self.attentions[ai](query, key, value, identity if self.pre_norm else None,
+                                            query_pos=query_pos, key_pos=key_pos, attn_mask=masks[ai],
+                                            key_padding_mask=key_padding_mask, **kwargs)
+                ai += 1
+                identity = query
+            elif op == "norm":
+                query = _fused_norm(self.norms[ni], query, None) if query.is_cuda else self.norms[ni](query)
+                ni += 1
+            else:
+                query = self.ffns[fi](query, identity if self.pre_norm else None)
+                fi += 1
+        return query
+
+
+class BEVFormerLayer(MyCustomBaseTransformerLayer):
+    """One encoder layer: temporal self-attention, spatial cross-attention, FFN, each followed by a
+    LayerNorm (encoder.py:242-406).  When a block is directly followed by ``norm`` (the post-norm
+    order every shipped config uses) its dropout + identity add are folded into the LayerNorm
+    kernel; any other order runs through the blocks' public forwards."""
+
+    def __init__(self, attn_cfgs, feedforward_channels, ffn_dropout=0.0, operation_order=None,
+                 act_cfg=dict(type="ReLU", inplace=True), norm_cfg=dict(type="LN"), ffn_num_fcs=2,
+                 **kwargs):
+        super().__init__(attn_cfgs=attn_cfgs, feedforward_channels=feedforward_channels,
+                         ffn_dropout=ffn_dropout, operation_order=operation_order, act_cfg=act_cfg,
+                         norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs, **kwargs)
+        self.fp16_enabled = False
+        assert len(self.operation_order) == 6
+        assert set(self.operation_order) == {"self_attn", "norm", "cross_attn", "ffn"}
+
+    def forward(self, query, key=None, value=None, bev_pos=None, query_pos=None, key_pos=None,
+                attn_masks=None, query_key_padding_mask=None, key_padding_mask=None, ref_2d=None,
+                ref_3d=None, bev_h=None, bev_w=None, reference_points_cam=None, mask=None,
+                spatial_shapes=None, level_start_index=None, prev_bev=None, **kwargs):
+        masks = self._attn_masks(attn_masks)
+        order = self.operation_order
+        ni = ai = fi = 0
+        identity = query
+        tsa_ss = kwargs.pop("tsa_spatial_shapes", None)
+        tsa_lsi = kwargs.pop("tsa_level_start_index", None)
+        if tsa_ss is None:                                    # (the reference rebuilds these per call)
+            tsa_ss = torch.tensor([[bev_h, bev_w]], device=query.device)
+            tsa_lsi = torch.tensor([0], device=query.device)
+        i = 0
+        while i < len(order):
+            op = order[i]
+            fuse = (not self.pre_norm) and i + 1 < len(order) and order[i + 1] == "norm" and query.is_cuda
+            if op == "self_attn":
+                att = self.attentions[ai]
+                if fuse and isinstance(att, TemporalSelfAttention) and att.batch_first:
+                    pre = att.attend(query, prev_bev, bev_pos, query_key_padding_mask, ref_2d,
+                                     tsa_ss, tsa_lsi)
+                    query = _fused_norm(self.norms[ni], att.dropout(pre), query)
+                    ni += 1
+                    i += 1
+                else:
+                    query = att(query, prev_bev, prev_bev, identity if self.pre_norm else None,
+                                query_pos=bev_pos, key_pos=bev_pos, attn_mask=masks[ai],
+                                key_padding_mask=query_key_padding_mask, reference_points=ref_2d,
+                                spatial_shapes=tsa_ss, level_start_index=tsa_lsi, **kwargs)
+                ai += 1
+                identity = query
+            elif op == "cross_attn":
+                att = self.attentions[ai]
+                if fuse and isinstance(att, SpatialCrossAttention) and query_pos is None:
+                    pre = att.attend(query, value if value is not None else key, reference_points_cam,
+                                     kwargs.get("bev_mask"), spatial_shapes, level_start_index,
+                                     kwargs.get("sca_plan"))
+                    query = _fused_norm(self.norms[ni], att.dropout(pre), query)
+                    ni += 1
+                    i += 1
+                else:
+                    query = att(query, key, value, identity if self.pre_norm else None,
+                                query_pos=query_pos, key_pos=key_pos, reference_points=ref_3d,
+                                reference_points_cam=reference_points_cam, mask=mask,
+                                attn_mask=masks[ai], key_padding_mask=key_padding_mask,
+                                spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                                **kwargs)
+                ai += 1
+                identity = query
+            elif op == "ffn":
+                ffn = self.ffns[fi]
+                if fuse and isinstance(ffn, FFN) and ffn.add_identity:
+                    pre = ffn.layers[ffn.num_fcs](ffn.transform(query))
+                    query = _fused_norm(self.norms[ni], pre, query)
+                    ni += 1
+                    i += 1
+                else:
+                    query = ffn(query, identity if self.pre_norm else None)
+                fi += 1
+            else:   # a norm that is not fused with the block before it
+                query = _fused_norm(self.norms[ni], query, None) if query.is_cuda else self.norms[ni](query)
+                ni += 1
+            i += 1
+        return query
+
+
+class BEVFormerEncoder(nn.Module):
+    """The stack of BEVFormerLayers plus the once-per-forward geometry (encoder.py:24-239).
+    Also stands in for mmcv's TransformerLayerSequence (deep-copies the layer config num_layers
+    times into ``self.layers``)."""
+
+    def __init__(self, *args, transformerlayers=None, num_layers=None, pc_range=None,
+                 num_points_in_pillar=4, return_intermediate=False, dataset_type="nuscenes",
+                 init_cfg=None, **kwargs):
+        super().__init__()
+        if args:   # positional (transformerlayers, num_layers) as TransformerLayerSequence allows
+            transformerlayers = args[0]
+            num_layers = args[1] if len(args) > 1 else num_layers
+        if isinstance(transformerlayers, dict):
+            transformerlayers = [copy.deepcopy(transformerlayers) for _ in range(num_layers)]
+        assert isinstance(transformerlayers, (list, tuple)) and len(transformerlayers) == num_layers
+        self.init_cfg = init_cfg
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList(build_transformer_layer(c) for c in transformerlayers)
+        self.embed_dims = self.layers[0].embed_dims
+        self.pre_norm = self.layers[0].pre_norm
+        self.return_intermediate = return_intermediate
+        self.num_points_in_pillar = num_points_in_pillar
+        self.pc_range = pc_range
+        self.fp16_enabled = False
+
+    # ---- geometry --------------------------------------------------------------------------------
+    @staticmethod
+    def get_reference_points(H, W, Z=8, num_points_in_pillar=4, dim="3d", bs=1, device="cuda",
+                             dtype=torch.float):
+        """Pillar anchors (bs, D, H*W, 3) for dim='3d', BEV grid (bs, H*W, 1, 2) for '2d', both
+        normalised to [0, 1] with q = i*W + j (encoder.py:46-85)."""
+        xs = torch.linspace(0.5, W - 0.5, W, dtype=dtype, device=device) / W
+        ys = torch.linspace(0.5, H - 0.5, H, dtype=dtype, device=device) / H
+        if dim == "3d":
+            zs = torch.linspace(0.5, Z - 0.5, num_points_in_pillar, dtype=dtype, device=device) / Z
+            d = num_points_in_pillar
+            pts = torch.stack([xs.view(1, 1, W).expand(d, H, W), ys.view(1, H, 1).expand(d, H, W),
+                               zs.view(d, 1, 1).expand(d, H, W)], -1)
+            return pts.reshape(1, d, H * W, 3).repeat(bs, 1, 1, 1)
+        if dim == "2d":
+            grid = torch.stack([xs.view(1, W).expand(H, W), ys.view(H, 1).expand(H, W)], -1)
+            return grid.reshape(1, H * W, 1, 2).repeat(bs, 1, 1, 1)
+        raise ValueError(dim)
+
+    def point_sampling(self, reference_points, pc_range, img_metas):
+        """Generic projection of arbitrary reference points (encoder.py:88-149), kept for API
+        compatibility; ``forward`` uses the fused kernel for the canonical pillar grid."""
+        l2i = reference_points.new_tensor(np.asarray([m["lidar2img"] for m in img_metas])).float()
+        ext = [pc_range[3] - pc_range[0], pc_range[4] - pc_range[1], pc_range[5] - pc_range[2]]
+        pts = torch.stack([reference_points[..., k] * ext[k] + pc_range[k] for k in range(3)], -1)
+        pts = torch.cat([pts, torch.ones_like(pts[..., :1])], -1).float()       # (B, D, Nq, 4)
+        b, d, nq = pts.shape[:3]
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            cam = torch.matmul(l2i.view(1, b, -1, 1, 4, 4),
+                               pts.permute(1, 0, 2, 3).reshape(d, b, 1, nq, 4, 1)).squeeze(-1)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        cam = cam.permute(2, 1, 3, 0, 4)                                        # (cam, B, Nq, D, 4)
+        eps = 1e-5
+        depth = cam[..., 2:3]
+        xy = cam[..., :2] / torch.clamp(depth, min=eps)
+        h, w = img_metas[0]["img_shape"][0][0], img_metas[0]["img_shape"][0][1]
+        xy = torch.stack([xy[..., 0] / w, xy[..., 1] / h], -1)
+        mask = ((depth > eps) & (xy[..., 1:2] > 0.0) & (xy[..., 1:2] < 1.0)
+                & (xy[..., 0:1] < 1.0) & (xy[..., 0:1] > 0.0)).squeeze(-1)
+        return xy, mask
+
+    def _camera_geometry(self, bs, bev_h, bev_w, img_metas, device):
+        """reference_points_cam (cam, bs, Nq, D, 2) f32 and bev_mask (cam, bs, Nq, D) bool through
+        the fused projection kernel (replaces get_reference_points('3d') + point_sampling)."""
+        l2i = torch.as_tensor(np.asarray([m["lidar2img"] for m in img_metas], dtype=np.float32))
+        l2i = l2i.to(device, non_blocking=True).contiguous()                    # (B, cam, 4, 4)
+        z_extent = self.pc_range[5] - self.pc_range[2]
+        z_norm = (torch.linspace(0.5, z_extent - 0.5, self.num_points_in_pillar) / z_extent).tolist()
+        h, w = img_metas[0]["img_shape"][0][0], img_metas[0]["img_shape"][0][1]   # quirk 10
+        return ops.point_sampling(l2i, self.pc_range, z_norm, h, w, bev_h, bev_w)
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, bev_query, key, value, *args, bev_h=None, bev_w=None, bev_pos=None,
+                spatial_shapes=None, level_start_index=None, valid_ratios=None, prev_bev=None,
+                shift=0.0, **kwargs):
+        """bev_query / bev_pos / prev_bev (Nq, bs, C); key = value (num_cams, S, bs, C);
+        returns (bs, Nq, C), or (num_layers, bs, Nq, C) with return_intermediate
+        (same contract as encoder.py:151-239)."""
+        bs = bev_query.size(1)
+        dev, dtype = bev_query.device, bev_query.dtype
+        ref_2d = self.get_reference_points(bev_h, bev_w, dim="2d", bs=bs, device=dev,
+                                           dtype=torch.float32)
+        if dev.type == "cuda":
+            ref_cam, bev_mask = self._camera_geometry(bs, bev_h, bev_w, kwargs["img_metas"], dev)
+        else:
+            ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
+                                               self.num_points_in_pillar, dim="3d", bs=bs,
+                                               device=dev, dtype=dtype)
+            ref_cam, bev_mask = self.point_sampling(ref_3d, self.pc_range, kwargs["img_metas"])
+        plan = kwargs.pop("sca_plan", None) or ScaPlan.build(bev_mask, ref_cam)
+
+        shift = torch.as_tensor(shift, device=dev, dtype=torch.float32)
+        shift_ref = ref_2d + (shift[:, None, None, :] if shift.dim() == 2 else shift)   # quirk 9
+        query = bev_query.permute(1, 0, 2)
+        pos = bev_pos.permute(1, 0, 2)
+        nq = query.shape[1]
+        if prev_bev is not None:   # quirk 8: the queue pairs prev_bev with the LAYER-0 input query
+            queue = torch.stack([prev_bev.permute(1, 0, 2), query], 1).reshape(bs * 2, nq, -1)
+            hybrid = torch.stack([shift_ref, ref_2d], 1).reshape(bs * 2, nq, 1, 2)
+        else:
+            queue = None
+            hybrid = torch.stack([ref_2d, ref_2d], 1).reshape(bs * 2, nq, 1, 2)
+        hybrid = hybrid.contiguous()
+        tsa_ss = torch.tensor([[bev_h, bev_w]], device=dev, dtype=torch.int64)
+        tsa_lsi = torch.zeros(1, device=dev, dtype=torch.int64)
+        ss = torch.as_tensor(spatial_shapes).to(device=dev, dtype=torch.int64).contiguous()
+        lsi = torch.as_tensor(level_start_index).to(device=dev, dtype=torch.int64).contiguous()
+
+        inter = []
+        for layer in self.layers:
+            query = layer(query, key, value, *args, bev_pos=pos, ref_2d=hybrid, ref_3d=None,
+                          bev_h=bev_h, bev_w=bev_w, spatial_shapes=ss, level_start_index=lsi,
+                          reference_points_cam=ref_cam, bev_mask=bev_mask, prev_bev=queue,
+                          sca_plan=plan, tsa_spatial_shapes=tsa_ss, tsa_level_start_index=tsa_lsi,
+                          **kwargs)
+            if self.return_intermediate:
+                inter.append(query)
+        return torch.stack(inter) if self.return_intermediate else query
+
+
+_register(TRANSFORMER_LAYER, MyCustomBaseTransformerLayer)
+_register(TRANSFORMER_LAYER, BEVFormerLayer)
+_register(TRANSFORMER_LAYER_SEQUENCE, BEVFormerEncoder)

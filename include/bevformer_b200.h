@@ -98,6 +98,113 @@ BEVF_API int bevf_msda_backward(const void *value, int value_dtype, const int64_
                        float *grad_loc, float *grad_attn, int B, int S, int M, int D, int Q, int L,
                        int P, void *stream);
 
+/*
+ * Row-list form of the sampler: R query rows, each sampling the value map named by row_map[r]
+ * (0 <= row_map[r] < B).  bevf_msda_forward is the special case row_map[r] = r / Q.
+ *
+ * replaces: the zero-padded per-camera re-batching around the op in
+ *   spatial_cross_attention.py:138-167 (nonzero -> max_len -> queries_rebatch -> op -> slots +=):
+ *   SpatialCrossAttention hands the op only the (camera, query) pairs that are actually in view,
+ *   in one launch, instead of num_cams x max_len padded rows.
+ *
+ *   loc (R, M, L, P, 2) f32; attn (R, M, L, P) f32; out / grad_out (R, M*D); row_map (R,) int32 DEVICE.
+ * Other arguments and semantics as for bevf_msda_forward / bevf_msda_backward.
+ */
+BEVF_API int bevf_msda_rows_forward(const void *value, int value_dtype, const int64_t *level_hw,
+                                    const int64_t *level_start, const float *loc, const float *attn,
+                                    void *out, int out_dtype, const int32_t *row_map, int B, int S,
+                                    int M, int D, int R, int L, int P, void *stream);
+
+BEVF_API int bevf_msda_rows_backward(const void *value, int value_dtype, const int64_t *level_hw,
+                                     const int64_t *level_start, const float *loc,
+                                     const float *attn, const void *grad_out, int grad_out_dtype,
+                                     float *grad_value, float *grad_loc, float *grad_attn,
+                                     const int32_t *row_map, int B, int S, int M, int D, int R,
+                                     int L, int P, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused memory-bound pieces of one encoder layer.  "raw" is the fp32 output of the layer's combined
+ * sampling_offsets|attention_weights GEMM, one row per BEV query.
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * SCA sampling points.  replaces spatial_cross_attention.py:338-372 (view, softmax over L*P,
+ * offset / (W_l, H_l), Z-anchor broadcast "point p uses anchor p mod D", add) for the in-view
+ * (camera, query) pairs only.
+ *   raw      (B*Nq, M*L*P*3) f32: [offsets (M,L,P,2) | logits (M,L*P)]
+ *   ref_cam  (ncam, B, Nq, D, 2) f32       pair_q, pair_cam (R,) int32
+ *   loc      (B*R, M, L, P, 2) f32 out      attn (B*R, M, L, P) f32 out   (row = b*R + r)
+ */
+BEVF_API int bevf_sca_prep_forward(const float *raw, const float *ref_cam, const int32_t *pair_q,
+                                   const int32_t *pair_cam, const int64_t *level_hw, float *loc,
+                                   float *attn, int B, int Nq, int R, int M, int L, int P, int D,
+                                   int ncam, void *stream);
+
+/* Backward of the above into d_raw (B*Nq, M*L*P*3) f32, fully overwritten; pair_of (ncam, Nq) int32
+ * holds the pair row of (camera, query) or -1. */
+BEVF_API int bevf_sca_prep_backward(const float *raw, const float *grad_loc, const float *grad_attn,
+                                    const int32_t *pair_of, const int64_t *level_hw, float *d_raw,
+                                    int B, int Nq, int R, int M, int L, int P, int ncam,
+                                    void *stream);
+
+/*
+ * TSA sampling points.  replaces temporal_self_attention.py:206-229 (view, softmax over L*P per
+ * queue entry, the two permute+reshape copies, offset / (W, H) + reference point).
+ *   raw    (B*Nq, M*2*L*P*3) f32: [offsets (M,2,L,P,2) | logits (M,2,L*P)]
+ *   ref2d  (B*2, Nq, L, 2) f32 (the encoder's hybird_ref_2d)
+ *   loc    (B*2, Nq, M, L, P, 2) f32 out     attn (B*2, Nq, M, L, P) f32 out
+ */
+BEVF_API int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const int64_t *level_hw,
+                                   float *loc, float *attn, int B, int Nq, int M, int L, int P,
+                                   void *stream);
+
+BEVF_API int bevf_tsa_prep_backward(const float *raw, const float *grad_loc, const float *grad_attn,
+                                    const int64_t *level_hw, float *d_raw, int B, int Nq, int M,
+                                    int L, int P, void *stream);
+
+/*
+ * y = LayerNorm(x + residual) * gamma + beta, optionally also y_plus_pos = y + pos.
+ * replaces the `norm` steps of BEVFormerLayer.forward (encoder.py:377-379) together with the
+ * preceding "+ identity" of the attention / FFN (temporal_self_attention.py:272,
+ * spatial_cross_attention.py:175, mmcv FFN) and TSA's `query + query_pos`
+ * (temporal_self_attention.py:186-187).  residual / pos / y_plus_pos / mean / rstd may be NULL.
+ * x, residual, pos, y, y_plus_pos: (rows, C) in `dtype`; gamma, beta, mean, rstd: f32. C in {256,512}.
+ */
+BEVF_API int bevf_layernorm_forward(const void *x, const void *residual, const float *gamma,
+                                    const float *beta, const void *pos, void *y, void *y_plus_pos,
+                                    float *mean, float *rstd, int64_t rows, int C, float eps,
+                                    int dtype, void *stream);
+
+/* dx (rows, C) is fully overwritten (it is also d residual); dgamma / dbeta (C,) f32 are
+ * ACCUMULATED INTO.  dy_plus_pos may be NULL. */
+BEVF_API int bevf_layernorm_backward(const void *x, const void *residual, const float *gamma,
+                                     const float *mean, const float *rstd, const void *dy,
+                                     const void *dy_plus_pos, void *dx, float *dgamma, float *dbeta,
+                                     int64_t rows, int C, int dtype, void *stream);
+
+/*
+ * slots[b,q,:] = inv_count[b,q] * sum_{cameras seeing q} out[b*R + pair_of[cam][q], :]
+ * replaces spatial_cross_attention.py:165-172 (python scatter-add loops, count, divide).
+ */
+BEVF_API int bevf_sca_combine_forward(const void *out, const int32_t *pair_of,
+                                      const float *inv_count, void *slots, int B, int Nq, int R,
+                                      int C, int ncam, int dtype, void *stream);
+
+BEVF_API int bevf_sca_combine_backward(const void *g_slots, const int32_t *pair_q,
+                                       const float *inv_count, void *g_out, int B, int Nq, int R,
+                                       int C, int dtype, void *stream);
+
+/*
+ * Projection of the pillar anchors into every camera + in-view mask, fp32 without FMA contraction.
+ * replaces BEVFormerEncoder.get_reference_points(dim='3d') + point_sampling (encoder.py:46-71,
+ * 88-149), including the 61 MB repeated-matrix materialisation.
+ *   lidar2img (B, ncam, 4, 4) f32 DEVICE; pc_range (6) and z_norm (D) HOST arrays;
+ *   ref_cam (ncam, B, Nq, D, 2) f32 out; bev_mask (ncam, B, Nq, D) uint8 out; Nq = bev_h*bev_w.
+ */
+BEVF_API int bevf_point_sampling(const float *lidar2img, const float *pc_range, const float *z_norm,
+                                 float img_h, float img_w, float *ref_cam, uint8_t *bev_mask, int B,
+                                 int ncam, int bev_h, int bev_w, int D, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

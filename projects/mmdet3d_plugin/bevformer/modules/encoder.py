@@ -1,0 +1,2 @@
+"""Drop-in module path: the implementation lives in bevformer_b200/plugin/encoder.py."""
+from bevformer_b200.plugin.encoder import BEVFormerEncoder, BEVFormerLayer  # noqa: F401

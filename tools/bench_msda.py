@@ -23,6 +23,50 @@ def alg_bytes(B, S, Q, M, L, P, sv, so, bwd):
     return fwd + B * S * C * 4 + B * Q * M * L * P * 12
 
 
+def rig_sca_inputs(dev):
+    """SCA sampler inputs with the REAL geometry: in-view (camera, query) pairs of the synthetic rig,
+    sampling points = projected pillar anchors + the reference's ring offsets (+ jitter)."""
+    import numpy as np
+    from bevformer_b200 import ops as _ops
+    from bevformer_b200.plugin import ScaPlan
+    w = syn.WORKLOADS["base"]
+    metas = syn.make_img_metas(w, 1)
+    l2i = torch.as_tensor(np.asarray([m["lidar2img"] for m in metas], dtype=np.float32)).to(dev)
+    z = (torch.linspace(0.5, 7.5, 4) / 8.0).tolist()
+    ref_cam, mask = _ops.point_sampling(l2i, syn.PC_RANGE, z, w.img_hw[0], w.img_hw[1], w.bev_h, w.bev_w)
+    plan = ScaPlan.build(mask, ref_cam)
+    sd = syn.make_state_dict(w)
+    g = torch.Generator().manual_seed(0)
+    nq, m, l, p = w.num_query, 8, 4, 8
+    raw = torch.cat([sd["layers.0.attentions.1.deformable_attention.sampling_offsets.bias"].view(1, -1)
+                     + 0.5 * torch.randn(nq, m * l * p * 2, generator=g),
+                     torch.randn(nq, m * l * p, generator=g)], 1).to(dev).contiguous()
+    ss = torch.tensor(w.levels, dtype=torch.int64, device=dev)
+    lsi = torch.tensor(w.level_start, dtype=torch.int64, device=dev)
+    loc, attn = _ops.sca_prep_forward(raw, plan.ref_cam, plan.pair_q, plan.pair_cam, ss, 1, nq, m, l, p)
+    value = torch.randn(6, w.num_value, 8, 32, generator=g).to(dev)
+    return value, ss, lsi, loc, attn, plan.row_map
+
+
+def rig_tsa_inputs(dev):
+    w = syn.WORKLOADS["base"]
+    sd = syn.make_state_dict(w)
+    g = torch.Generator().manual_seed(0)
+    nq, m, p = w.num_query, 8, 4
+    from bevformer_b200 import ops as _ops
+    raw = torch.cat([sd["layers.0.attentions.0.sampling_offsets.bias"].view(1, -1)
+                     + 0.5 * torch.randn(nq, m * 2 * p * 2, generator=g),
+                     torch.randn(nq, m * 2 * p, generator=g)], 1).to(dev).contiguous()
+    ys, xs = torch.meshgrid(torch.arange(200.0), torch.arange(200.0), indexing="ij")
+    ref = torch.stack([(xs + 0.5) / 200, (ys + 0.5) / 200], -1).reshape(1, nq, 1, 2)
+    ref = torch.cat([ref + torch.tensor([0.01, -0.02]), ref], 0).to(dev).contiguous()
+    ss = torch.tensor([[200, 200]], dtype=torch.int64, device=dev)
+    lsi = torch.zeros(1, dtype=torch.int64, device=dev)
+    loc, attn = _ops.tsa_prep_forward(raw, ref, ss, 1, nq, m, 1, p)
+    value = torch.randn(2, nq, 8, 32, generator=g).to(dev)
+    return value, ss, lsi, loc, attn
+
+
 def time_op(fn, iters, flush):
     ev = [(torch.cuda.Event(True), torch.cuda.Event(True)) for _ in range(iters)]
     for i in range(3):
@@ -39,6 +83,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--profile", action="store_true", help="launch each kernel once (for ncu)")
     args = ap.parse_args()
     dev = "cuda"
     w = syn.WORKLOADS["base"]
@@ -67,6 +112,10 @@ def main():
             g = torch.randn_like(out)
             gv = torch.zeros(v.shape, device=dev, dtype=torch.float32)
             sz = 4 if dt == torch.float32 else 2
+            if args.profile:
+                ops.msda_backward(vd, ss, lsi, loc, attn, g, gv)
+                torch.cuda.synchronize()
+                continue
             t_f, t_fmin = time_op(lambda: ops.msda_forward(vd, ss, lsi, loc, attn), args.iters, flush)
             t_b, t_bmin = time_op(lambda: ops.msda_backward(vd, ss, lsi, loc, attn, g, gv),
                                   args.iters, flush)
@@ -74,6 +123,47 @@ def main():
             r = dict(shape=name, dtype=str(dt).split(".")[-1], fwd_ms=round(t_f, 4), bwd_ms=round(t_b, 4),
                      fwd_min_ms=round(t_fmin, 4), bwd_min_ms=round(t_bmin, 4),
                      fwd_alg_MB=round(bf / 1e6, 1), bwd_alg_MB=round(bb / 1e6, 1),
+                     fwd_GBs=round(bf / t_f / 1e6, 1), bwd_GBs=round(bb / t_b / 1e6, 1),
+                     fwd_frac=round(bf / t_f / 1e6 / hbm, 4), bwd_frac=round(bb / t_b / 1e6 / hbm, 4))
+            print(json.dumps(r), flush=True)
+            res.append(r)
+    # ---- the same kernels on the real geometry (what the encoder actually launches)
+    for name in ("sca_rig", "tsa_rig"):
+        if args.only and args.only not in name:
+            continue
+        if name == "sca_rig":
+            v, ss, lsi, loc, attn, row_map = rig_sca_inputs(dev)
+            R = loc.shape[0]
+        else:
+            v, ss, lsi, loc, attn = rig_tsa_inputs(dev)
+            row_map = None
+        B, S, M, _ = v.shape
+        L, P = loc.shape[-3], loc.shape[-2]
+        Q = loc.shape[0] if row_map is not None else loc.shape[1]
+        nrows = Q if row_map is not None else B * Q
+        for dt in (torch.float32, torch.bfloat16):
+            vd = v.to(dt)
+            if row_map is not None:
+                fwd = lambda: ops.msda_rows_forward(vd, ss, lsi, loc, attn, row_map)
+            else:
+                fwd = lambda: ops.msda_forward(vd, ss, lsi, loc, attn)
+            out = fwd()
+            g = torch.randn_like(out)
+            gv = torch.zeros(v.shape, device=dev, dtype=torch.float32)
+            if row_map is not None:
+                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv)
+            else:
+                bwd = lambda: ops.msda_backward(vd, ss, lsi, loc, attn, g, gv)
+            if args.profile:
+                bwd(); torch.cuda.synchronize(); continue
+            sz = 4 if dt == torch.float32 else 2
+            t_f, t_fmin = time_op(fwd, args.iters, flush)
+            t_b, t_bmin = time_op(bwd, args.iters, flush)
+            C = M * 32
+            bf = B * S * C * sz + nrows * M * L * P * 12 + nrows * C * sz
+            bb = bf + B * S * C * 4 + nrows * M * L * P * 12
+            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], fwd_ms=round(t_f, 4),
+                     bwd_ms=round(t_b, 4), fwd_alg_MB=round(bf / 1e6, 1), bwd_alg_MB=round(bb / 1e6, 1),
                      fwd_GBs=round(bf / t_f / 1e6, 1), bwd_GBs=round(bb / t_b / 1e6, 1),
                      fwd_frac=round(bf / t_f / 1e6 / hbm, 4), bwd_frac=round(bb / t_b / 1e6 / hbm, 4))
             print(json.dumps(r), flush=True)

@@ -7,7 +7,7 @@
 namespace bevf {
 
 constexpr int kEThreads = 256;
-constexpr int kMaxLP = 64;        // num_levels * num_points per head handled in registers
+
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -45,12 +45,12 @@ sca_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref_cam,
     float *lo = loc + t * LP * 2;
     float *at = attn + t * LP;
     for (int l = 0; l < L; ++l) {
-        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        const float fw = (float)level_hw[2 * l + 1], fh = (float)level_hw[2 * l];
         for (int p = 0; p < P; ++p) {
             const int k = l * P + p, z = p % D;          // point p uses Z-anchor p mod D (quirk 3)
             const float2 o = *reinterpret_cast<const float2 *>(off + 2 * k);
             const float2 rf = *reinterpret_cast<const float2 *>(rc + 2 * z);
-            *reinterpret_cast<float2 *>(lo + 2 * k) = make_float2(rf.x + o.x * iw, rf.y + o.y * ih);
+            *reinterpret_cast<float2 *>(lo + 2 * k) = make_float2(rf.x + __fdiv_rn(o.x, fw), rf.y + __fdiv_rn(o.y, fh));
             at[k] = __expf(lg[k] - mx) * inv;
         }
     }
@@ -91,7 +91,7 @@ sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
         dot += __expf(lg[k] - mx) * inv * ga;
     }
     for (int l = 0; l < L; ++l) {
-        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        const float fw = (float)level_hw[2 * l + 1], fh = (float)level_hw[2 * l];
         for (int p = 0; p < P; ++p) {
             const int k = l * P + p;
             float ga = 0.f, gx = 0.f, gy = 0.f;
@@ -103,7 +103,7 @@ sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
             }
             const float a = __expf(lg[k] - mx) * inv;
             d_lg[k] = a * (ga - dot);
-            *reinterpret_cast<float2 *>(d_off + 2 * k) = make_float2(gx * iw, gy * ih);
+            *reinterpret_cast<float2 *>(d_off + 2 * k) = make_float2(__fdiv_rn(gx, fw), __fdiv_rn(gy, fh));
         }
     }
 }
@@ -137,12 +137,12 @@ tsa_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref2d,
     float *lo = loc + (orow * M + m) * LP * 2;
     float *at = attn + (orow * M + m) * LP;
     for (int l = 0; l < L; ++l) {
-        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        const float fw = (float)level_hw[2 * l + 1], fh = (float)level_hw[2 * l];
         const float rx = rf[2 * l], ry = rf[2 * l + 1];
         for (int p = 0; p < P; ++p) {
             const int k = l * P + p;
             const float2 o = *reinterpret_cast<const float2 *>(off + 2 * k);
-            *reinterpret_cast<float2 *>(lo + 2 * k) = make_float2(rx + o.x * iw, ry + o.y * ih);
+            *reinterpret_cast<float2 *>(lo + 2 * k) = make_float2(rx + __fdiv_rn(o.x, fw), ry + __fdiv_rn(o.y, fh));
             at[k] = __expf(lg[k] - mx) * inv;
         }
     }
@@ -175,13 +175,13 @@ tsa_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
     float dot = 0.f;
     for (int k = 0; k < LP; ++k) dot += __expf(lg[k] - mx) * inv * ga[k];
     for (int l = 0; l < L; ++l) {
-        const float iw = 1.f / (float)level_hw[2 * l + 1], ih = 1.f / (float)level_hw[2 * l];
+        const float fw = (float)level_hw[2 * l + 1], fh = (float)level_hw[2 * l];
         for (int p = 0; p < P; ++p) {
             const int k = l * P + p;
             const float a = __expf(lg[k] - mx) * inv;
             d_raw[o_lg + k] = a * (ga[k] - dot);
             const float2 g2 = *reinterpret_cast<const float2 *>(gl + 2 * k);
-            *reinterpret_cast<float2 *>(d_raw + o_off + 2 * k) = make_float2(g2.x * iw, g2.y * ih);
+            *reinterpret_cast<float2 *>(d_raw + o_off + 2 * k) = make_float2(__fdiv_rn(g2.x, fw), __fdiv_rn(g2.y, fh));
         }
     }
 }

@@ -1,0 +1,528 @@
+// Dense projections of the encoder layer on the 5th-generation tensor cores (sm_100a only).
+//
+//   Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])        bf16 in, fp32 accumulate
+//
+// replaces the cuBLAS GEMM + separate bias/ReLU/residual kernels behind every nn.Linear of
+// TemporalSelfAttention / MSDeformableAttention3D / SpatialCrossAttention / mmcv FFN
+// (temporal_self_attention.py:198,206-209,267; spatial_cross_attention.py:173,334,338-341;
+// custom_base_transformer_layer.py:157-158).
+//
+// Structure (one CTA per SM, persistent over 128 x BN output tiles):
+//   warp 0     TMA producer: cp.async.bulk.tensor loads of the A (128 x 64) and B (BN x 64) k-blocks
+//              into a ring of SWIZZLE_128B shared-memory stages, completion on mbarriers
+//   warp 1     MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
+//              K=16) x 4 per k-block, accumulating in TMEM; tcgen05.commit releases the smem stage
+//              and, at the end of a tile, publishes the accumulator
+//   warp 2     TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-7  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one TMEM lane = one output row per
+//              thread), add bias / residual, ReLU, convert, 16 B stores; the double-buffered TMEM
+//              lets the MMA of tile i+1 run under the epilogue of tile i.
+// These GEMMs have K = 256 or 512 only: they are bound by streaming X / Y through HBM, so the tile
+// is sized for full-width rows (BN up to 256) rather than for tensor-pipe peak.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace bevf {
+
+constexpr int kBM = 128;           // rows per tile == TMEM lanes
+constexpr int kBK = 64;            // bf16 elements per k-block row == 128 B == one swizzle atom
+constexpr int kGemmThreads = 256;
+constexpr int kAccStages = 2;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row
+// groups 1024 B apart (SBO), version 1 (Blackwell), layout type 2.  (Bit layout: CuTe
+// cute/arch/mma_sm100_desc.hpp, union SmemDescriptor.)
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);            // start address  [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                           // LBO (unused)   [16,30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // SBO            [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                           // version        [46,48)
+    d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B   [61,64)
+    return d;
+}
+
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+struct GemmParams {
+    int M, N, K;
+    int BN;                // output-tile width (multiple of 16, <= 256, divides N)
+    int stages;            // smem ring depth
+    int relu;
+    const float *bias;     // (N) or null
+    const bf16 *residual;  // (M, N) or null
+    void *y;               // (M, N) bf16 or fp32
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_nt_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+             const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve-up: [stages x (A 16 KB | B BN*128 B)] [barriers] [tmem ptr]
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = kBM * 128, b_bytes = p.BN * 128, stage_bytes = a_bytes + b_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *empty = full + p.stages;
+    uint64_t *acc_full = empty + p.stages;
+    uint64_t *acc_empty = acc_full + kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + kBM - 1) / kBM, tiles_n = p.N / p.BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int kblocks = p.K / kBK;
+    const uint32_t tmem_cols = (kAccStages * p.BN <= 32) ? 32 : (kAccStages * p.BN <= 64) ? 64
+                             : (kAccStages * p.BN <= 128) ? 128 : (kAccStages * p.BN <= 256) ? 256 : 512;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int tm = t / tiles_n, tn = t % tiles_n;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *sa = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    tma_load_2d(sa, &map_a, &full[s], kb * kBK, tm * kBM);
+                    tma_load_2d(sa + a_bytes, &map_b, &full[s], kb * kBK, tn * p.BN);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16(kBM, p.BN);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t da = smem_desc_k_sw128(a_addr), db = smem_desc_k_sw128(a_addr + a_bytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16 B units
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&empty[s]);                       // frees the smem stage when the MMAs retire
+                    if (kb == kblocks - 1) umma_commit(&acc_full[as]);   // accumulator complete
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+                if (++as == kAccStages) { as = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                                    // TMEM lane quarter of this warp
+        int as = 0; uint32_t aph = 0;
+        TO *y = reinterpret_cast<TO *>(p.y);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int tm = t / tiles_n, tn = t % tiles_n;
+            const int row = tm * kBM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                const int col = tn * p.BN + c0;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + col + i));
+                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (row_ok) {
+                    if (p.residual) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + (size_t)row * p.N + col);
+                        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        const uint32_t u[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { v[2 * i] += bf16_lo(u[i]); v[2 * i + 1] += bf16_hi(u[i]); }
+                    }
+                    TO *dst = y + (size_t)row * p.N + col;
+                    if constexpr (sizeof(TO) == 2) {
+                        uint4 o0, o1;
+                        o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+                        o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+                        o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+                        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                        reinterpret_cast<uint4 *>(dst)[0] = o0;
+                        reinterpret_cast<uint4 *>(dst)[1] = o1;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            reinterpret_cast<float4 *>(dst)[i / 4] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (++as == kAccStages) { as = 0; aph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+
+// ================================================================================================
+// Weight gradient:  dW[N, K] += dY[M, N]^T . X[M, K]      (reduction over the M rows)
+//
+// Both operands are read in their natural row-major layout, which makes them MN-major for this
+// product (the non-reduced index is the contiguous one): TMA boxes of 64 columns x 64 rows land in
+// shared memory exactly as the UMMA "MN-major, SWIZZLE_128B" canonical layout wants them
+// (64 contiguous MN elements = 128 B per K row, 8-row groups 1024 B apart = SBO, successive
+// 64-column chunks one box (8 KB) apart = LBO).  The reduction is split over CTAs (split-M); every
+// CTA adds its 128 x BN partial tile into dW with 16 B fp32 reductions.
+// ================================================================================================
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t chunk_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(chunk_bytes >> 4) << 16;            // LBO: next 64-element MN chunk
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // SBO: next group of 8 K rows
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+struct WgradParams {
+    int M, N, K;           // dY (M, N), X (M, K), dW (N, K)
+    int BN;                // tile width along K (multiple of 64, <= 256, divides K)
+    int stages;
+    int rows_per_split;    // multiple of 64
+    int splits;
+    float *dw;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wgrad_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kChunk = 64 * 128;                               // one 64 x 64 bf16 box
+    const int a_bytes = 2 * kChunk, b_bytes = (p.BN / 64) * kChunk, stage_bytes = a_bytes + b_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *empty = full + p.stages;
+    uint64_t *acc_full = empty + p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (p.N + kBM - 1) / kBM, tiles_k = p.K / p.BN;
+    const int units = tiles_n * tiles_k * p.splits;
+    const uint32_t tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    int s = 0; uint32_t ph = 0;          // smem ring state (producer and MMA walk it identically)
+    uint32_t aph = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u % p.splits, tile = u / p.splits;
+        const int tn = tile / tiles_k, tk = tile % tiles_k;
+        const int m_begin = split * p.rows_per_split;
+        const int m_end = min(p.M, m_begin + p.rows_per_split);
+        const int kblocks = (m_end - m_begin + 63) / 64;
+        if (warp == 0 && lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t *sa = smem + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                const int m0 = m_begin + kb * 64;
+                tma_load_2d(sa, &map_dy, &full[s], tn * kBM, m0);
+                tma_load_2d(sa + kChunk, &map_dy, &full[s], tn * kBM + 64, m0);
+                for (int c = 0; c < p.BN / 64; ++c)
+                    tma_load_2d(sa + a_bytes + c * kChunk, &map_x, &full[s], tk * p.BN + c * 64, m0);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // MN-major A and B: instruction-descriptor bits 15 and 16
+            const uint32_t idesc = instr_desc_bf16(kBM, p.BN) | (1u << 15) | (1u << 16);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t da = smem_desc_mn_sw128(a_addr, kChunk), db = smem_desc_mn_sw128(a_addr + a_bytes, kChunk);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // 16 reduction rows further = 2048 B = 128 in 16 B units
+                    umma_bf16(tmem_base, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc,
+                              (uint32_t)((kb | k) != 0));
+                }
+                umma_commit(&empty[s]);
+                if (kb == kblocks - 1) umma_commit(acc_full);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+        // every warp waits for the accumulator of this unit; warps 4-7 drain it
+        if (kblocks > 0) {
+            if (warp >= 4) {
+                mbar_wait(acc_full, aph);
+                tc_fence_after();
+                const int q = warp & 3;
+                const int row = tn * kBM + q * 32 + lane;          // output row = N index
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    if (row < p.N) {
+                        float *dst = p.dw + (size_t)row * p.K + tk * p.BN + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                       __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    }
+                }
+                tc_fence_before();
+            }
+            aph ^= 1;
+        }
+        __syncthreads();   // the accumulator is reused by the next unit: drain before the next MMA
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static int make_map_2d(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    // row-major (rows, cols) bf16; box = box_rows x 64 elements (128 B inner), SWIZZLE_128B
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(uint16_t)};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims,
+                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int pick_bn(int N) {
+    for (int bn : {256, 192, 128, 64}) if (N % bn == 0) return bn;
+    if (N <= 256 && N % 16 == 0) return N;
+    for (int bn = 240; bn >= 16; bn -= 16) if (N % bn == 0) return bn;
+    return 0;
+}
+
+}  // namespace bevf
+
+using namespace bevf;
+
+extern "C" int bevf_linear_forward(const void *x, const void *w, const float *bias, const void *residual,
+                                   void *y, int y_dtype, int64_t M, int N, int K, int relu, void *stream) {
+    const char *who = "bevf_linear_forward";
+    if (M < 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
+    if (M == 0) return 0;
+    if (!x || !w || !y) return fail("%s: null pointer argument", who);
+    if (K % kBK != 0) return fail("%s: K must be a multiple of 64 (got %lld)", who, K);
+    if (N % 16 != 0) return fail("%s: N must be a multiple of 16 (got %lld)", who, N);
+    if (M >= (1ll << 31)) return fail("%s: M too large", who);
+    if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias)) ||
+        (residual && !aligned16(residual)))
+        return fail("%s: pointers must be 16-byte aligned", who);
+    if (y_dtype != BEVF_DTYPE_BF16 && y_dtype != BEVF_DTYPE_F32) return fail("%s: unsupported dtype code", who);
+    const int bn = pick_bn(N);
+    if (bn == 0) return fail("%s: no tile width divides N", who);
+
+    CUtensorMap map_a, map_b;
+    if (int e = make_map_2d(&map_a, x, (uint64_t)M, (uint64_t)K, kBM))
+        return fail("%s: cuTensorMapEncodeTiled(A) failed (%lld)", who, e);
+    if (int e = make_map_2d(&map_b, w, (uint64_t)N, (uint64_t)K, (uint32_t)bn))
+        return fail("%s: cuTensorMapEncodeTiled(B) failed (%lld)", who, e);
+
+    GemmParams p;
+    p.M = (int)M; p.N = N; p.K = K; p.BN = bn; p.relu = relu;
+    p.bias = bias; p.residual = reinterpret_cast<const bf16 *>(residual); p.y = y;
+    const int stage_bytes = (kBM + bn) * 128;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages > K / kBK * 2) stages = K / kBK * 2;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 2 * kAccStages) * 8 + 16;
+
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_nt_bf16<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(gemm_nt_bf16<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    const int tiles = (int)((M + kBM - 1) / kBM) * (N / bn);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (y_dtype == BEVF_DTYPE_BF16)
+        gemm_nt_bf16<bf16><<<grid, kGemmThreads, smem, st>>>(map_a, map_b, p);
+    else
+        gemm_nt_bf16<float><<<grid, kGemmThreads, smem, st>>>(map_a, map_b, p);
+    return check_launch(who);
+}
+
+
+extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64_t M, int N, int K,
+                                 void *stream) {
+    const char *who = "bevf_linear_wgrad";
+    if (M < 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
+    if (M == 0) return 0;
+    if (!dy || !x || !dw) return fail("%s: null pointer argument", who);
+    if (K % 64 != 0 || N % 8 != 0) return fail("%s: K must be a multiple of 64 and N of 8", who);
+    if (M >= (1ll << 31)) return fail("%s: M too large", who);
+    if (!aligned16(dy) || !aligned16(x) || !aligned16(dw)) return fail("%s: pointers must be 16-byte aligned", who);
+    int bn = 0;
+    for (int c : {256, 192, 128, 64}) if (K % c == 0) { bn = c; break; }
+    CUtensorMap map_dy, map_x;
+    if (int e = make_map_2d(&map_dy, dy, (uint64_t)M, (uint64_t)N, 64))
+        return fail("%s: cuTensorMapEncodeTiled(dY) failed (%lld)", who, e);
+    if (int e = make_map_2d(&map_x, x, (uint64_t)M, (uint64_t)K, 64))
+        return fail("%s: cuTensorMapEncodeTiled(X) failed (%lld)", who, e);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_wgrad_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    WgradParams p;
+    p.M = (int)M; p.N = N; p.K = K; p.BN = bn; p.dw = dw;
+    const int tiles = ((N + kBM - 1) / kBM) * (K / bn);
+    int splits = (2 * num_sms + tiles - 1) / tiles;                // ~2 units per SM
+    int rows = (int)((M + splits - 1) / splits);
+    rows = ((rows + 63) / 64) * 64;
+    splits = (int)((M + rows - 1) / rows);
+    p.rows_per_split = rows; p.splits = splits;
+    const int stage_bytes = 2 * 8192 + (bn / 64) * 8192;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 1) * 8 + 16;
+    const int units = tiles * splits;
+    const int grid = units < num_sms ? units : num_sms;
+    gemm_wgrad_bf16<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_dy, map_x, p);
+    return check_launch(who);
+}

@@ -41,7 +41,9 @@ struct Corner {
 // Range test in float BEFORE any int conversion: projected anchors behind a camera reach |x| ~ 1e9.
 __device__ __forceinline__ Corner make_corner(float locx, float locy, int H, int W) {
     Corner c;
-    float x = locx * (float)W - 0.5f, y = locy * (float)H - 0.5f;
+    // unfused multiply / add: the sampling cell is floor(x), so x must round exactly like the
+    // reference expression loc * W - 0.5 (an FMA would flip floor() for samples on a cell boundary)
+    float x = __fadd_rn(__fmul_rn(locx, (float)W), -0.5f), y = __fadd_rn(__fmul_rn(locy, (float)H), -0.5f);
     c.valid = (x > -1.f) && (y > -1.f) && (x < (float)W) && (y < (float)H);
     if (!c.valid) { x = 0.f; y = 0.f; }
     const float xf = floorf(x), yf = floorf(y);
@@ -268,6 +270,19 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     uint4 gh = make_uint4(0, 0, 0, 0);            // the same slice as packed bf16, for FHFMA dots
     if constexpr (kHalfDot)
         gh = __ldg(reinterpret_cast<const uint4 *>(grad_out + row * 32 + sub * VEC));
+    // Scatter layout.  A 16 B reduction covers 4 fp32 channels.  With VEC == 8 the lane's own
+    // channels [8 sub, 8 sub + 8) would make each of its two reductions hit every other 16 B of the
+    // row (half-filled sectors); instead reduction r of lane `sub` takes channels
+    // [16 r + 4 sub, 16 r + 4 sub + 4), so one instruction writes 64 contiguous bytes per row.
+    constexpr int NRED = VEC / 4;
+    float gr[NRED][4];
+    if constexpr (NRED == 1) {
+        gr[0][0] = g[0]; gr[0][1] = g[1]; gr[0][2] = g[2]; gr[0][3] = g[3];
+    } else {
+#pragma unroll
+        for (int r = 0; r < NRED; ++r) load_vec<TG, 4>(grad_out + row * 32 + 16 * r + 4 * sub, gr[r]);
+    }
+    const int red_shift = (NRED == 1) ? 0 : (4 * sub - sub * VEC);   // from the lane's load offset
 
     for (int s0 = 0; s0 < LP; s0 += LANES) {
         // ---- produce
@@ -317,13 +332,14 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
                 d[j][0] = v00.dot(g); d[j][1] = v01.dot(g); d[j][2] = v10.dot(g); d[j][3] = v11.dot(g);
             }
             // scatter w * a * g with 16 B reductions; zero-weight corners are skipped
-            float *gv = grad_value + o00;
+            float *gv = grad_value + o00 + red_shift;
 #pragma unroll
-            for (int i = 0; i < VEC; i += 4) {
-                if (q00 != 0.f) red_add_v4(gv + i, q00 * g[i], q00 * g[i + 1], q00 * g[i + 2], q00 * g[i + 3]);
-                if (q01 != 0.f) red_add_v4(gv + ox + i, q01 * g[i], q01 * g[i + 1], q01 * g[i + 2], q01 * g[i + 3]);
-                if (q10 != 0.f) red_add_v4(gv + oy + i, q10 * g[i], q10 * g[i + 1], q10 * g[i + 2], q10 * g[i + 3]);
-                if (q11 != 0.f) red_add_v4(gv + oy + ox + i, q11 * g[i], q11 * g[i + 1], q11 * g[i + 2], q11 * g[i + 3]);
+            for (int r = 0; r < NRED; ++r) {
+                float *gp = gv + 16 * r;
+                if (q00 != 0.f) red_add_v4(gp, q00 * gr[r][0], q00 * gr[r][1], q00 * gr[r][2], q00 * gr[r][3]);
+                if (q01 != 0.f) red_add_v4(gp + ox, q01 * gr[r][0], q01 * gr[r][1], q01 * gr[r][2], q01 * gr[r][3]);
+                if (q10 != 0.f) red_add_v4(gp + oy, q10 * gr[r][0], q10 * gr[r][1], q10 * gr[r][2], q10 * gr[r][3]);
+                if (q11 != 0.f) red_add_v4(gp + oy + ox, q11 * gr[r][0], q11 * gr[r][1], q11 * gr[r][2], q11 * gr[r][3]);
             }
         }
         // ---- reduce-scatter the dots over the group: lane `sub` ends with the totals of sample

@@ -445,3 +445,41 @@ def point_sampling(lidar2img, pc_range, z_norm, img_h, img_w, bev_h, bev_w):
                                      _stream_ptr(lidar2img))
     _lib.check(st, lib)
     return ref_cam, mask.bool()
+
+
+def linear_tc(x, weight, bias=None, residual=None, relu=False, out_dtype=None):
+    """y = act(x @ weight.T + bias) (+ residual) on the tcgen05 GEMM.  x (..., K) bf16, weight (N, K)
+    bf16, bias (N) any float dtype, residual (..., N) bf16; returns (..., N) bf16 or fp32."""
+    _need_cuda(x, "x")
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise RuntimeError("linear_tc: x and weight must be bfloat16")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    M = x.numel() // K
+    w = weight.contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    res = None if residual is None else residual.contiguous()
+    out_dtype = out_dtype or torch.bfloat16
+    y = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=out_dtype)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = lib.bevf_linear_forward(x.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(res), y.data_ptr(),
+                                     _DT[out_dtype], M, N, K, int(bool(relu)), _stream_ptr(x))
+    _lib.check(st, lib)
+    return y
+
+
+def linear_wgrad_tc(dy, x):
+    """dW = dy^T @ x on the tcgen05 split-M kernel. dy (M, N) bf16, x (M, K) bf16 -> (N, K) fp32."""
+    _need_cuda(dy, "dy")
+    _need_cuda(x, "x")
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.shape[0] != x.shape[0]:
+        raise RuntimeError("linear_wgrad_tc: dy (M,N) and x (M,K) must be bfloat16 with equal M")
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.zeros((N, K), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = lib.bevf_linear_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, N, K, _stream_ptr(x))
+    _lib.check(st, lib)
+    return dw

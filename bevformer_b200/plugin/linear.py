@@ -1,22 +1,69 @@
-"""The dense projections of the encoder layer (value_proj / output_proj / the combined
-sampling_offsets|attention_weights head / FFN), as one function so that the backing kernel can be
-swapped in one place.
+"""The dense projections of the encoder layer (value_proj / output_proj / the stacked
+sampling_offsets|attention_weights head / FFN) behind one function.
 
-Backing: cuBLASLt through torch for now (a plain library GEMM, bias fused by the library).  The
-tcgen05 kernel with fused epilogues replaces it behind this same function.
+bf16 CUDA inputs run on the hand-written tcgen05 kernel of ``csrc/gemm.cu`` (bias, ReLU and the fp32
+result of the offsets|logits head fused into its epilogue); its backward uses the same kernel for
+dX = dY . W and, until the transposed-operand variant lands, the library GEMM for dW = dY^T . X.
+fp32 inputs (the fp32 parity configuration) use the library GEMM.  ``BEVF_GEMM=cublas`` forces the
+library path everywhere (A/B measurement).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
+from torch.autograd.function import Function, once_differentiable
+
+from .. import ops
+
+
+def _use_tc(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.shape[1] % 64 == 0
+            and weight.shape[0] % 16 == 0 and os.environ.get("BEVF_GEMM", "tc") != "cublas")
+
+
+class _LinearTC(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, fp32_out):
+        w = weight.to(torch.bfloat16)
+        xc = x.contiguous()
+        y = ops.linear_tc(xc, w, bias, None, relu, torch.float32 if fp32_out else torch.bfloat16)
+        ctx.save_for_backward(xc, w, y if relu else None)
+        ctx.has_bias = bias is not None
+        ctx.dtypes = (weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        k, n = w.shape[1], w.shape[0]
+        dy2 = dy.reshape(-1, n)
+        if y is not None:                                  # ReLU: gradient only where the output is > 0
+            dy2 = dy2 * (y.reshape(-1, n) > 0)
+        dy2 = dy2.to(torch.bfloat16).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_tc(dy2, w.t().contiguous(), None, None, False).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.mm(dy2.t(), x.reshape(-1, k)).to(ctx.dtypes[0])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0, dtype=torch.float32).to(ctx.dtypes[1])
+        return dx, dw, db, None, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False) -> torch.Tensor:
+    if _use_tc(x, weight):
+        return _LinearTC.apply(x, weight, bias, relu, False)
     y = F.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
     return F.relu(y, inplace=True) if relu else y
 
 
 def linear_fp32_out(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
-    """Projection whose result is consumed in fp32 (sampling offsets / attention logits)."""
+    """Projection whose result is consumed in fp32 (sampling offsets / attention logits): taken
+    straight from the fp32 accumulator on the tcgen05 path."""
+    if _use_tc(x, weight):
+        return _LinearTC.apply(x, weight, bias, False, True)
     y = F.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
     return y.float()

@@ -205,6 +205,29 @@ BEVF_API int bevf_point_sampling(const float *lidar2img, const float *pc_range, 
                                  float img_h, float img_w, float *ref_cam, uint8_t *bev_mask, int B,
                                  int ncam, int bev_h, int bev_w, int D, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dense projection on the tcgen05 tensor cores:
+ *     y[M,N] = act( x[M,K] . w[N,K]^T + bias[N] ) (+ residual[M,N])
+ * replaces nn.Linear (cuBLAS GEMM + bias) and the ReLU / "+ identity" launches that follow it in
+ * TemporalSelfAttention (temporal_self_attention.py:198,206-209,267), MSDeformableAttention3D /
+ * SpatialCrossAttention (spatial_cross_attention.py:334,338-341,173) and mmcv's FFN.
+ *   x (M,K) bf16, w (N,K) bf16 (nn.Linear layout), bias (N) f32 or NULL, residual (M,N) bf16 or NULL,
+ *   y (M,N) in y_dtype (bf16 | f32, straight from the fp32 accumulator).  relu != 0 applies
+ *   max(.,0) before the residual add.  K % 64 == 0, N % 16 == 0.
+ */
+BEVF_API int bevf_linear_forward(const void *x, const void *w, const float *bias, const void *residual,
+                                 void *y, int y_dtype, int64_t M, int N, int K, int relu,
+                                 void *stream);
+
+/*
+ * Weight gradient of the projection above:  dw[N,K] += dy[M,N]^T . x[M,K]   (fp32, ACCUMULATED
+ * INTO: the caller zero-fills).  dy, x bf16 row-major; split over the M rows across the SMs, partial
+ * tiles combined with 16 B fp32 reductions.  replaces the cuBLAS call autograd makes for
+ * nn.Linear.weight.grad.  K % 64 == 0, N % 8 == 0.
+ */
+BEVF_API int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64_t M, int N, int K,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

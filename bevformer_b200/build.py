@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if f.read().strip() == digest:
                 return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH, *sources(), "-lcuda"]
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH, *sources()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:

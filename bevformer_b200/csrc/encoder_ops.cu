@@ -108,6 +108,182 @@ sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative SCA prep for num_heads == 8: one warp per row, lane = (head m = lane / 4,
+// quarter sub = lane % 4), each lane owns PPL = L*P/4 consecutive sampling points of its head.
+// Every global access is a 16 B vector and a quad covers a head's contiguous 32*PPL/8.. bytes, so
+// the warp reads / writes whole 128 B lines; the softmax reduces over the quad with two shuffles.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+template <int N> __device__ __forceinline__ void ldv(const float *p, float (&v)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(p + i));
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            const float2 t = __ldg(reinterpret_cast<const float2 *>(p + i));
+            v[i] = t.x; v[i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = __ldg(p + i);
+    }
+}
+template <int N> __device__ __forceinline__ void stv(float *p, const float (&v)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) *reinterpret_cast<float4 *>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) *reinterpret_cast<float2 *>(p + i) = make_float2(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = v[i];
+    }
+}
+
+template <int PPL>
+__global__ void __launch_bounds__(kEThreads)
+sca_prep_fwd_m8(const float *__restrict__ raw, const float *__restrict__ ref_cam,
+                const int *__restrict__ pair_q, const int *__restrict__ pair_cam,
+                const int64_t *__restrict__ level_hw, float *__restrict__ loc, float *__restrict__ attn,
+                int B, int Nq, int R, int L, int P, int D, int pmagic) {
+    constexpr int M = 8;
+    __shared__ float s_w[16], s_h[16];
+    if ((int)threadIdx.x < L) { s_h[threadIdx.x] = (float)level_hw[2 * threadIdx.x]; s_w[threadIdx.x] = (float)level_hw[2 * threadIdx.x + 1]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, m = lane >> 2, sub = lane & 3;
+    const long long t = (long long)blockIdx.x * (kEThreads / 32) + (threadIdx.x >> 5);   // row b*R + r
+    if (t >= (long long)B * R) return;
+    const int r = (int)(t % R), b = (int)(t / R);
+    const int q = __ldg(pair_q + r), cam = __ldg(pair_cam + r);
+    const int LP = 4 * PPL, k0 = sub * PPL;
+    const float *rq = raw + ((long long)b * Nq + q) * (M * LP * 3);
+    float lg[PPL], off[2 * PPL];
+    ldv<PPL>(rq + M * LP * 2 + m * LP + k0, lg);
+    ldv<2 * PPL>(rq + (m * LP + k0) * 2, off);
+    float mx = lg[0];
+#pragma unroll
+    for (int i = 1; i < PPL; ++i) mx = fmaxf(mx, lg[i]);
+    mx = quad_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) { lg[i] = __expf(lg[i] - mx); sum += lg[i]; }
+    const float inv = 1.f / quad_sum(sum);
+    const float *rc = ref_cam + (((long long)cam * B + b) * Nq + q) * D * 2;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+        const int k = k0 + i;
+        const int l = (k * pmagic) >> 16;                  // k / P
+        const int z = (k - l * P) % D;
+        const float2 rf = __ldg(reinterpret_cast<const float2 *>(rc) + z);
+        off[2 * i] = rf.x + __fdiv_rn(off[2 * i], s_w[l]);
+        off[2 * i + 1] = rf.y + __fdiv_rn(off[2 * i + 1], s_h[l]);
+        lg[i] *= inv;
+    }
+    stv<2 * PPL>(loc + ((t * M + m) * LP + k0) * 2, off);
+    stv<PPL>(attn + (t * M + m) * LP + k0, lg);
+}
+
+template <int PPL>
+__global__ void __launch_bounds__(kEThreads)
+sca_prep_bwd_m8(const float *__restrict__ raw, const float *__restrict__ grad_loc,
+                const float *__restrict__ grad_attn, const int *__restrict__ pair_of,
+                const int64_t *__restrict__ level_hw, float *__restrict__ d_raw, int B, int Nq, int R,
+                int L, int P, int ncam, int pmagic) {
+    constexpr int M = 8;
+    __shared__ float s_w[16], s_h[16];
+    if ((int)threadIdx.x < L) { s_h[threadIdx.x] = (float)level_hw[2 * threadIdx.x]; s_w[threadIdx.x] = (float)level_hw[2 * threadIdx.x + 1]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, m = lane >> 2, sub = lane & 3;
+    const long long bq = (long long)blockIdx.x * (kEThreads / 32) + (threadIdx.x >> 5);
+    if (bq >= (long long)B * Nq) return;
+    const int q = (int)(bq % Nq), b = (int)(bq / Nq);
+    const int LP = 4 * PPL, k0 = sub * PPL;
+    const long long rbase = bq * (M * LP * 3);
+    float a[PPL];
+    ldv<PPL>(raw + rbase + M * LP * 2 + m * LP + k0, a);
+    float mx = a[0];
+#pragma unroll
+    for (int i = 1; i < PPL; ++i) mx = fmaxf(mx, a[i]);
+    mx = quad_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) { a[i] = __expf(a[i] - mx); sum += a[i]; }
+    const float inv = 1.f / quad_sum(sum);
+    float ga[PPL], gl[2 * PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) { ga[i] = 0.f; gl[2 * i] = 0.f; gl[2 * i + 1] = 0.f; }
+    for (int c = 0; c < ncam; ++c) {
+        const int r = __ldg(pair_of + (long long)c * Nq + q);          // warp-uniform
+        if (r < 0) continue;
+        const long long s = (((long long)b * R + r) * M + m) * LP + k0;
+        float t1[PPL], t2[2 * PPL];
+        ldv<PPL>(grad_attn + s, t1);
+        ldv<2 * PPL>(grad_loc + 2 * s, t2);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) { ga[i] += t1[i]; gl[2 * i] += t2[2 * i]; gl[2 * i + 1] += t2[2 * i + 1]; }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) { a[i] *= inv; dot += a[i] * ga[i]; }
+    dot = quad_sum(dot);
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+        const int k = k0 + i;
+        const int l = (k * pmagic) >> 16;
+        ga[i] = a[i] * (ga[i] - dot);
+        gl[2 * i] = __fdiv_rn(gl[2 * i], s_w[l]);
+        gl[2 * i + 1] = __fdiv_rn(gl[2 * i + 1], s_h[l]);
+    }
+    stv<PPL>(d_raw + rbase + M * LP * 2 + m * LP + k0, ga);
+    stv<2 * PPL>(d_raw + rbase + (m * LP + k0) * 2, gl);
+}
+
+// column sums of a (rows, C) matrix into fp32 (bias gradients): out[c] += sum_r x[r, c]
+template <typename T>
+__global__ void __launch_bounds__(kEThreads)
+colsum_kernel(const T *__restrict__ x, float *__restrict__ out, long long rows, int C, int rows_per_cta) {
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    const int per_row = C / VEC;                       // vectors per row
+    // thread -> (column vector cv, row lane rl); consecutive threads walk along a row (coalesced)
+    const int cv = threadIdx.x % per_row, rl = threadIdx.x / per_row, rstep = kEThreads / per_row;
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min(rows, r0 + rows_per_cta);
+    if (rl < rstep) {
+        for (long long r = r0 + rl; r < r1; r += rstep) {
+            float v[VEC];
+            load_vec<T, VEC>(x + r * C + cv * VEC, v);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] += v[k];
+        }
+    }
+    extern __shared__ float s_part[];                  // C floats
+    for (int i = threadIdx.x; i < C; i += kEThreads) s_part[i] = 0.f;
+    __syncthreads();
+    if (rl < rstep) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) atomicAdd(&s_part[cv * VEC + k], acc[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += kEThreads) atomicAdd(out + i, s_part[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // TSA sampling-point preparation.  raw row: [ offsets (M, 2, L, P, 2) | logits (M, 2, L*P) ]
 // out rows ordered (b, queue j, q): loc (B*2, Nq, M, L, P, 2), attn (B*2, Nq, M, L, P)
@@ -439,8 +615,21 @@ extern "C" int bevf_sca_prep_forward(const float *raw, const float *ref_cam, con
     const long long total = (long long)B * R * M;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && ref_cam && pair_q && pair_cam && level_hw && loc && attn, who, "null pointer argument");
-    sca_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
-        raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, M, L, P, D, ncam);
+    const int LP = L * P, pmagic = (65536 + P - 1) / P;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned wgrid = blocks_for((long long)B * R, kEThreads / 32);
+    if (M == 8 && L <= 16 && LP * P < 65536 && (LP == 4 || LP == 8 || LP == 16 || LP == 32 || LP == 64)) {
+        switch (LP / 4) {
+            case 1: sca_prep_fwd_m8<1><<<wgrid, kEThreads, 0, st>>>(raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, L, P, D, pmagic); break;
+            case 2: sca_prep_fwd_m8<2><<<wgrid, kEThreads, 0, st>>>(raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, L, P, D, pmagic); break;
+            case 4: sca_prep_fwd_m8<4><<<wgrid, kEThreads, 0, st>>>(raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, L, P, D, pmagic); break;
+            case 8: sca_prep_fwd_m8<8><<<wgrid, kEThreads, 0, st>>>(raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, L, P, D, pmagic); break;
+            default: sca_prep_fwd_m8<16><<<wgrid, kEThreads, 0, st>>>(raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, L, P, D, pmagic); break;
+        }
+    } else {
+        sca_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, st>>>(
+            raw, ref_cam, pair_q, pair_cam, level_hw, loc, attn, B, Nq, R, M, L, P, D, ncam);
+    }
     return check_launch(who);
 }
 
@@ -453,8 +642,21 @@ extern "C" int bevf_sca_prep_backward(const float *raw, const float *grad_loc,
     const long long total = (long long)B * Nq * M;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && pair_of && level_hw && d_raw && (R == 0 || (grad_loc && grad_attn)), who, "null pointer argument");
-    sca_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
-        raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, M, L, P, ncam);
+    const int LP = L * P, pmagic = (65536 + P - 1) / P;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned wgrid = blocks_for((long long)B * Nq, kEThreads / 32);
+    if (M == 8 && L <= 16 && LP * P < 65536 && (LP == 4 || LP == 8 || LP == 16 || LP == 32 || LP == 64)) {
+        switch (LP / 4) {
+            case 1: sca_prep_bwd_m8<1><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
+            case 2: sca_prep_bwd_m8<2><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
+            case 4: sca_prep_bwd_m8<4><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
+            case 8: sca_prep_bwd_m8<8><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
+            default: sca_prep_bwd_m8<16><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
+        }
+    } else {
+        sca_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, st>>>(
+            raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, M, L, P, ncam);
+    }
     return check_launch(who);
 }
 
@@ -594,5 +796,25 @@ extern "C" int bevf_point_sampling(const float *lidar2img, const float *pc_range
     prm.img_h = img_h; prm.img_w = img_w;
     point_sampling_kernel<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
         lidar2img, prm, ref_cam, bev_mask, B, ncam, bev_h, bev_w, D);
+    return check_launch(who);
+}
+
+
+extern "C" int bevf_colsum(const void *x, float *out, int64_t rows, int C, int dtype, void *stream) {
+    const char *who = "bevf_colsum";
+    BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
+    if (rows == 0) return 0;
+    BEVF_REQUIRE(x && out, who, "null pointer argument");
+    const int vec = dtype == BEVF_DTYPE_BF16 ? 8 : 4;
+    BEVF_REQUIRE(dtype == BEVF_DTYPE_BF16 || dtype == BEVF_DTYPE_F32, who, "unsupported dtype code");
+    BEVF_REQUIRE(C % vec == 0 && C / vec <= kEThreads, who, "C must be a multiple of the vector width and <= 2048");
+    long long rows_per_cta = (rows + 148 * 4 - 1) / (148 * 4);
+    if (rows_per_cta < 64) rows_per_cta = 64;
+    const unsigned grid = blocks_for(rows, (int)rows_per_cta);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BEVF_DTYPE_BF16)
+        colsum_kernel<bf16><<<grid, kEThreads, C * sizeof(float), st>>>((const bf16 *)x, out, rows, C, (int)rows_per_cta);
+    else
+        colsum_kernel<float><<<grid, kEThreads, C * sizeof(float), st>>>((const float *)x, out, rows, C, (int)rows_per_cta);
     return check_launch(who);
 }

@@ -483,3 +483,16 @@ def linear_wgrad_tc(dy, x):
         st = lib.bevf_linear_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, N, K, _stream_ptr(x))
     _lib.check(st, lib)
     return dw
+
+
+def colsum(x):
+    """fp32 column sums of a (rows, C) tensor (bias gradients)."""
+    _need_cuda(x, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.zeros(C, device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = lib.bevf_colsum(x.data_ptr(), out.data_ptr(), rows, C, _DT[x.dtype], _stream_ptr(x))
+    _lib.check(st, lib)
+    return out

@@ -3,7 +3,8 @@ sampling_offsets|attention_weights head / FFN) behind one function.
 
 bf16 CUDA inputs run on the hand-written tcgen05 kernel of ``csrc/gemm.cu`` (bias, ReLU and the fp32
 result of the offsets|logits head fused into its epilogue); its backward uses the same kernel for
-dX = dY . W and, until the transposed-operand variant lands, the library GEMM for dW = dY^T . X.
+dX = dY . W and the split-M tcgen05 kernel for dW = dY^T . X (``BEVF_WGRAD=cublas`` switches that one
+back to the library); bias gradients come from the column-sum kernel.
 fp32 inputs (the fp32 parity configuration) use the library GEMM.  ``BEVF_GEMM=cublas`` forces the
 library path everywhere (A/B measurement).
 """
@@ -47,9 +48,12 @@ class _LinearTC(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_tc(dy2, w.t().contiguous(), None, None, False).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = torch.mm(dy2.t(), x.reshape(-1, k)).to(ctx.dtypes[0])
+            if os.environ.get("BEVF_WGRAD", "tc") != "cublas" and n % 8 == 0:
+                dw = ops.linear_wgrad_tc(dy2, x.reshape(-1, k)).to(ctx.dtypes[0])
+            else:
+                dw = torch.mm(dy2.t(), x.reshape(-1, k)).to(ctx.dtypes[0])
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(0, dtype=torch.float32).to(ctx.dtypes[1])
+            db = ops.colsum(dy2).to(ctx.dtypes[1])
         return dx, dw, db, None, None
 
 

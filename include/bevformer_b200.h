@@ -228,6 +228,10 @@ BEVF_API int bevf_linear_forward(const void *x, const void *w, const float *bias
 BEVF_API int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64_t M, int N, int K,
                                void *stream);
 
+/* out[c] += sum over rows of x[r, c]  (fp32, ACCUMULATED INTO).  The bias gradient of the projections:
+ * replaces the at::reduce_kernel autograd launches for nn.Linear.bias.grad.  x (rows, C) f32 | bf16. */
+BEVF_API int bevf_colsum(const void *x, float *out, int64_t rows, int C, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

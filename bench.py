@@ -298,7 +298,9 @@ def run_ours(args):
                                "(116x200..15x25), D=4 pillar points, TSA with prev_bev, fwd+bwd, train mode "
                                "(dropout 0.1), 1 sample per GPU" + (", DDP gradient all-reduce (NCCL)" if world > 1 else ""),
                    "l2": "per-step working set (>1 GB of activations + 95 MB features) exceeds the 126 MB L2; no explicit flush",
-                   "gemm_backend": "cuBLASLt via torch (library GEMM)"},
+                   "gemm_backend": ("cuBLASLt via torch (library GEMM; BEVF_GEMM=cublas)"
+                                    if os.environ.get("BEVF_GEMM", "tc") == "cublas" else
+                                    "hand-written tcgen05 kernels (csrc/gemm.cu): forward, dX and split-M dW")},
         "e2e": {"value": total_q / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

@@ -597,6 +597,98 @@ point_sampling_kernel(const float *__restrict__ lidar2img, PointSamplingParams p
     mask[o] = ok ? 1 : 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative TSA prep for num_heads == 8: one warp per (b, q); lane = (head m = lane / 4,
+// queue entry j = (lane / 2) % 2, half = lane % 2); a lane owns PPL = L*P/2 points; the softmax over
+// the L*P points of one (head, queue entry) reduces over the lane pair.
+// ------------------------------------------------------------------------------------------------
+template <int PPL, bool kBackward>
+__global__ void __launch_bounds__(kEThreads)
+tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
+            const float *__restrict__ grad_loc, const float *__restrict__ grad_attn,
+            const int64_t *__restrict__ level_hw, float *__restrict__ loc, float *__restrict__ attn,
+            float *__restrict__ d_raw, int B, int Nq, int L, int P, int pmagic) {
+    constexpr int M = 8;
+    __shared__ float s_w[16], s_h[16];
+    if ((int)threadIdx.x < L) { s_h[threadIdx.x] = (float)level_hw[2 * threadIdx.x]; s_w[threadIdx.x] = (float)level_hw[2 * threadIdx.x + 1]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, m = lane >> 2, j = (lane >> 1) & 1, half = lane & 1;
+    const long long bq = (long long)blockIdx.x * (kEThreads / 32) + (threadIdx.x >> 5);
+    if (bq >= (long long)B * Nq) return;
+    const int q = (int)(bq % Nq), b = (int)(bq / Nq);
+    const int LP = 2 * PPL, k0 = half * PPL;
+    const long long rbase = bq * (M * 2 * LP * 3);
+    const long long o_off = rbase + ((m * 2 + j) * LP + k0) * 2;
+    const long long o_lg = rbase + M * 2 * LP * 2 + (m * 2 + j) * LP + k0;
+    const long long orow = ((long long)b * 2 + j) * Nq + q;
+    const long long o_out = (orow * M + m) * LP + k0;
+    float a[PPL];
+    ldv<PPL>(raw + o_lg, a);
+    float mx = a[0];
+#pragma unroll
+    for (int i = 1; i < PPL; ++i) mx = fmaxf(mx, a[i]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) { a[i] = __expf(a[i] - mx); sum += a[i]; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) a[i] *= inv;
+    if constexpr (!kBackward) {
+        float off[2 * PPL];
+        ldv<2 * PPL>(raw + o_off, off);
+        const float *rf = ref2d + orow * L * 2;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            const int l = ((k0 + i) * pmagic) >> 16;
+            off[2 * i] = __ldg(rf + 2 * l) + __fdiv_rn(off[2 * i], s_w[l]);
+            off[2 * i + 1] = __ldg(rf + 2 * l + 1) + __fdiv_rn(off[2 * i + 1], s_h[l]);
+        }
+        stv<2 * PPL>(loc + 2 * o_out, off);
+        stv<PPL>(attn + o_out, a);
+    } else {
+        float ga[PPL], gl[2 * PPL];
+        ldv<PPL>(grad_attn + o_out, ga);
+        ldv<2 * PPL>(grad_loc + 2 * o_out, gl);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) dot += a[i] * ga[i];
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            const int l = ((k0 + i) * pmagic) >> 16;
+            ga[i] = a[i] * (ga[i] - dot);
+            gl[2 * i] = __fdiv_rn(gl[2 * i], s_w[l]);
+            gl[2 * i + 1] = __fdiv_rn(gl[2 * i + 1], s_h[l]);
+        }
+        stv<PPL>(d_raw + o_lg, ga);
+        stv<2 * PPL>(d_raw + o_off, gl);
+    }
+}
+
+template <bool kBackward>
+static bool launch_tsa_prep_m8(const float *raw, const float *ref2d, const float *grad_loc,
+                               const float *grad_attn, const int64_t *level_hw, float *loc, float *attn,
+                               float *d_raw, int B, int Nq, int M, int L, int P, cudaStream_t st) {
+    const int LP = L * P;
+    if (!(M == 8 && L <= 16 && LP * P < 65536 && (LP == 2 || LP == 4 || LP == 8 || LP == 16 || LP == 32)))
+        return false;
+    const int pmagic = (65536 + P - 1) / P;
+    const unsigned grid = (unsigned)(((long long)B * Nq + kEThreads / 32 - 1) / (kEThreads / 32));
+#define BEVF_TSA_CASE(N) tsa_prep_m8<N, kBackward><<<grid, kEThreads, 0, st>>>(raw, ref2d, grad_loc, grad_attn, level_hw, loc, attn, d_raw, B, Nq, L, P, pmagic)
+    switch (LP / 2) {
+        case 1: BEVF_TSA_CASE(1); break;
+        case 2: BEVF_TSA_CASE(2); break;
+        case 4: BEVF_TSA_CASE(4); break;
+        case 8: BEVF_TSA_CASE(8); break;
+        default: BEVF_TSA_CASE(16); break;
+    }
+#undef BEVF_TSA_CASE
+    return true;
+}
+
 }  // namespace bevf
 
 using namespace bevf;
@@ -668,8 +760,10 @@ extern "C" int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const
     const long long total = (long long)B * Nq * M * 2;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && ref2d && level_hw && loc && attn, who, "null pointer argument");
-    tsa_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
-        raw, ref2d, level_hw, loc, attn, B, Nq, M, L, P);
+    if (!launch_tsa_prep_m8<false>(raw, ref2d, nullptr, nullptr, level_hw, loc, attn, nullptr, B, Nq, M, L, P,
+                                   (cudaStream_t)stream))
+        tsa_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+            raw, ref2d, level_hw, loc, attn, B, Nq, M, L, P);
     return check_launch(who);
 }
 
@@ -681,8 +775,10 @@ extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
     const long long total = (long long)B * Nq * M * 2;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && grad_loc && grad_attn && level_hw && d_raw, who, "null pointer argument");
-    tsa_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
-        raw, grad_loc, grad_attn, level_hw, d_raw, B, Nq, M, L, P);
+    if (!launch_tsa_prep_m8<true>(raw, nullptr, grad_loc, grad_attn, level_hw, nullptr, nullptr, d_raw, B, Nq, M,
+                                  L, P, (cudaStream_t)stream))
+        tsa_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+            raw, grad_loc, grad_attn, level_hw, d_raw, B, Nq, M, L, P);
     return check_launch(who);
 }
 

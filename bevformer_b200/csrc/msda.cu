@@ -22,6 +22,8 @@
 //     are reduce-scattered over the group so that the lane that produced the sample's scalars also
 //     finishes grad_loc / grad_attn.  grad_value is scattered with 16 B vector reductions
 //     (REDG.E.ADD.F32x4), never scalar atomics.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bevf {
@@ -163,7 +165,7 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const int64_t *__restrict__ level_start, const float *__restrict__ loc,
              const float *__restrict__ attn, TO *__restrict__ out,
              const int *__restrict__ row_map, int S, int M, int Q, int L, int P, int magic,
-             long long rows) {
+             int iters, long long rows) {
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
     constexpr bool kHalf = (VEC == 8);
     __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
@@ -171,7 +173,11 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
-    long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * G + grp;
+    // a warp walks `iters` consecutive groups of G rows: a CTA then covers 8 * iters * G rows, i.e.
+    // a run of neighbouring queries whose image footprints overlap in L1
+    for (int it = 0; it < iters; ++it) {
+    long long row = (((long long)blockIdx.x * (kThreads / 32) + warp) * iters + it) * G + grp;
+    if (row - grp >= rows) break;                 // warp-uniform
     const bool live = row < rows;                 // dead groups still take part in the shuffles
     if (!live) row = rows - 1;
     const int m = (int)(row % M);
@@ -234,6 +240,7 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
         }
     }
     if (live) store_vec<TO, VEC>(out + row * 32 + sub * VEC, acc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -246,7 +253,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const float *__restrict__ attn, const TG *__restrict__ grad_out,
              float *__restrict__ grad_value, float *__restrict__ grad_loc,
              float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M, int Q,
-             int L, int P, int magic, long long rows) {
+             int L, int P, int magic, int iters, long long rows) {
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
     constexpr bool kHalfDot = (VEC == 8) && (sizeof(TG) == 2);
     __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
@@ -254,7 +261,9 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
-    long long row = ((long long)blockIdx.x * (kThreads / 32) + warp) * G + grp;
+    for (int it = 0; it < iters; ++it) {
+    long long row = (((long long)blockIdx.x * (kThreads / 32) + warp) * iters + it) * G + grp;
+    if (row - grp >= rows) break;                 // warp-uniform
     const bool live = row < rows;
     if (!live) row = rows - 1;
     const int m = (int)(row % M);
@@ -370,6 +379,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             reinterpret_cast<float2 *>(grad_loc)[si] = make_float2((float)Wm * gx, (float)Hm * gy);
         }
     }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -469,6 +479,19 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+// rows handled per warp: BEVF_MSDA_ITERS overrides (experiments); default 8 once there is enough
+// work to keep >= 4 CTAs per SM busy, else 1.
+static int pick_iters(long long rows, int G) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("BEVF_MSDA_ITERS");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) return forced;
+    const long long per_block = (long long)(kThreads / 32) * G;
+    return rows >= per_block * 8 * 148 * 4 ? 8 : 1;
+}
+
 static int check_dims(const char *who, int B, int S, int M, int D, int Q, int L, int P) {
     if (B < 0 || S < 0 || M <= 0 || D <= 0 || Q < 0 || L <= 0 || P <= 0)
         return fail("%s: negative or zero dimension", who);
@@ -485,10 +508,12 @@ static int launch_fwd(const char *who, const void *value, const int64_t *hw, con
                       int M, int D, int Q, int L, int P, long long rows, cudaStream_t st) {
     if (D == 32) {
         constexpr int G = Vec<T>::N;      // rows per warp == channels per lane (4 or 8)
-        const long long per_block = (long long)(kThreads / 32) * G;
+        const int iters = pick_iters(rows, G);
+        const long long per_block = (long long)(kThreads / 32) * G * iters;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
         msda_fwd_d32<T, TO><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn, (TO *)out,
-                                                       row_map, S, M, Q, L, P, (65536 + P - 1) / P, rows);
+                                                       row_map, S, M, Q, L, P, (65536 + P - 1) / P, iters,
+                                                       rows);
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
         msda_fwd_generic<T, TO><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
@@ -504,11 +529,12 @@ static int launch_bwd(const char *who, const void *value, const int64_t *hw, con
                       long long rows, cudaStream_t st) {
     if (D == 32) {
         constexpr int G = Vec<T>::N;
-        const long long per_block = (long long)(kThreads / 32) * G;
+        const int iters = pick_iters(rows, G);
+        const long long per_block = (long long)(kThreads / 32) * G * iters;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
         msda_bwd_d32<T, TG><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
                                                        (const TG *)go, gv, gl, ga, row_map, S, M, Q,
-                                                       L, P, (65536 + P - 1) / P, rows);
+                                                       L, P, (65536 + P - 1) / P, iters, rows);
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
         msda_bwd_generic<T, TG><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,

@@ -364,7 +364,7 @@ class BEVFormerEncoder(nn.Module):
                                                self.num_points_in_pillar, dim="3d", bs=bs,
                                                device=dev, dtype=dtype)
             ref_cam, bev_mask = self.point_sampling(ref_3d, self.pc_range, kwargs["img_metas"])
-        plan = kwargs.pop("sca_plan", None) or ScaPlan.build(bev_mask, ref_cam)
+        plan = kwargs.pop("sca_plan", None) or ScaPlan.build(bev_mask, ref_cam, (bev_h, bev_w))
 
         shift = torch.as_tensor(shift, device=dev, dtype=torch.float32)
         shift_ref = ref_2d + (shift[:, None, None, :] if shift.dim() == 2 else shift)   # quirk 9

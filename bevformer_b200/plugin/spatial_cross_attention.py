@@ -14,6 +14,7 @@ camera), and the sampler runs over the pair list in a single launch with no padd
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -39,19 +40,30 @@ class ScaPlan:
     num_pairs: int
 
     @staticmethod
-    def build(bev_mask: torch.Tensor, reference_points_cam: torch.Tensor) -> "ScaPlan":
+    def build(bev_mask: torch.Tensor, reference_points_cam: torch.Tensor, bev_hw=None,
+              tile: int = 8) -> "ScaPlan":
         """bev_mask (ncam, bs, Nq, D) bool.  Quirk 1: the pair list comes from
         batch item 0's mask for every batch item (:139), the divisor from each item's own mask
-        (:169-171)."""
+        (:169-171).  With ``bev_hw`` the pairs of each camera are ordered in tile x tile BEV patches
+        (row-major inside a patch) instead of plain row-major: the sampler's CTAs then work on compact
+        patches whose image footprints overlap in L1.  The order is immaterial to the result (the
+        combine step gathers through ``pair_of``)."""
         ncam, bs, nq, _ = bev_mask.shape
         seen = bev_mask.any(-1)                                 # (ncam, bs, Nq)
         hit0 = seen[:, 0]
         nz = hit0.nonzero()                                     # the one host sync (sizes the lists)
         r = int(nz.shape[0])
+        if bev_hw is not None and tile > 1 and os.environ.get("BEVF_SCA_TILE", "1") != "0":
+            h, w = bev_hw
+            qi, qj = nz[:, 1] // w, nz[:, 1] % w
+            tiles_x = (w + tile - 1) // tile
+            key = ((nz[:, 0] * ((h + tile - 1) // tile) + qi // tile) * tiles_x + qj // tile) * (tile * tile) \
+                + (qi % tile) * tile + qj % tile
+            nz = nz[torch.argsort(key)]
         pair_cam = nz[:, 0].to(torch.int32).contiguous()
         pair_q = nz[:, 1].to(torch.int32).contiguous()
         pair_of = torch.full((ncam, nq), -1, dtype=torch.int32, device=bev_mask.device)
-        pair_of[hit0] = torch.arange(r, dtype=torch.int32, device=bev_mask.device)
+        pair_of[pair_cam.long(), pair_q.long()] = torch.arange(r, dtype=torch.int32, device=bev_mask.device)
         inv_count = 1.0 / seen.sum(0).clamp(min=1).to(torch.float32)
         row_map = (torch.arange(bs, device=bev_mask.device, dtype=torch.int32)[:, None] * ncam
                    + pair_cam[None, :]).reshape(-1).contiguous()

@@ -34,7 +34,7 @@ def rig_sca_inputs(dev):
     l2i = torch.as_tensor(np.asarray([m["lidar2img"] for m in metas], dtype=np.float32)).to(dev)
     z = (torch.linspace(0.5, 7.5, 4) / 8.0).tolist()
     ref_cam, mask = _ops.point_sampling(l2i, syn.PC_RANGE, z, w.img_hw[0], w.img_hw[1], w.bev_h, w.bev_w)
-    plan = ScaPlan.build(mask, ref_cam)
+    plan = ScaPlan.build(mask, ref_cam, (w.bev_h, w.bev_w) if os.environ.get("BENCH_TILE", "1") == "1" else None)
     sd = syn.make_state_dict(w)
     g = torch.Generator().manual_seed(0)
     nq, m, l, p = w.num_query, 8, 4, 8

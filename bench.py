@@ -117,12 +117,19 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -130,14 +137,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.05)]
+        if len(rows) < 3:                       # very short timed region: fall back to every sample taken
+            rows = [r for _, r in self.rows]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -244,16 +254,18 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    sampler.mark_begin()
     ops.KERNEL_TIMERS["msda_rows_backward"] = []
     ops.KERNEL_TIMERS["msda_rows_forward"] = []
     launches0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - launches0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     kt = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.KERNEL_TIMERS.items()}
     ops.KERNEL_TIMERS.clear()

@@ -382,6 +382,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     }
 }
 
+
 // ------------------------------------------------------------------------------------------------
 // any head_dim: one warp per (query, head) row, lanes stride over channels
 // ------------------------------------------------------------------------------------------------
@@ -479,17 +480,15 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-// rows handled per warp: BEVF_MSDA_ITERS overrides (experiments); default 8 once there is enough
-// work to keep >= 4 CTAs per SM busy, else 1.
+// row groups handled per warp: 1; BEVF_MSDA_ITERS overrides (experiments).
 static int pick_iters(long long rows, int G) {
     static int forced = -1;
     if (forced < 0) {
         const char *e = getenv("BEVF_MSDA_ITERS");
         forced = e ? atoi(e) : 0;
     }
-    if (forced > 0) return forced;
-    const long long per_block = (long long)(kThreads / 32) * G;
-    return rows >= per_block * 8 * 148 * 4 ? 8 : 1;
+    (void)rows; (void)G;
+    return forced > 0 ? forced : 1;   // measured (profiles/README.md): >1 loses parallelism, no L1 gain
 }
 
 static int check_dims(const char *who, int B, int S, int M, int D, int Q, int L, int P) {

@@ -155,7 +155,7 @@ def main():
             else:
                 bwd = lambda: ops.msda_backward(vd, ss, lsi, loc, attn, g, gv)
             if args.profile:
-                bwd(); torch.cuda.synchronize(); continue
+                fwd(); bwd(); torch.cuda.synchronize(); continue
             sz = 4 if dt == torch.float32 else 2
             t_f, t_fmin = time_op(fwd, args.iters, flush)
             t_b, t_bmin = time_op(bwd, args.iters, flush)

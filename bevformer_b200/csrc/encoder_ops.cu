@@ -2,6 +2,8 @@
 // sampler).  Each kernel replaces a run of ATen launches in the reference; see the per-function
 // comments in include/bevformer_b200.h for the Python lines.  All are HBM-bound streaming kernels:
 // 16 B vector accesses, one pass over each tensor, fp32 math.
+#include <curand_kernel.h>
+
 #include "common.cuh"
 
 namespace bevf {
@@ -367,12 +369,32 @@ tsa_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
 // One warp per row; a lane holds C/32 channels in registers (C <= 1024, C % 128 == 0 fast path for
 // 16 B accesses).  Statistics in fp32; eps inside the sqrt.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int C>
+// Keep-mask of the fused dropout: Philox4x32-10 keyed by (seed, row * 32 + lane); element i of the
+// lane's PER channels uses draw i.  Forward and backward regenerate the same bits, nothing is stored.
+template <int PER>
+__device__ __forceinline__ void dropout_scale(float (&m)[PER], unsigned long long seed, long long row, int lane,
+                                              float p) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)row * 32ull + (unsigned long long)lane, 0ull, &st);
+    const float scale = 1.f / (1.f - p);
+#pragma unroll
+    for (int i = 0; i < PER; i += 4) {
+        const float4 u = curand_uniform4(&st);
+        m[i] = u.x >= p ? scale : 0.f; m[i + 1] = u.y >= p ? scale : 0.f;
+        m[i + 2] = u.z >= p ? scale : 0.f; m[i + 3] = u.w >= p ? scale : 0.f;
+    }
+}
+
+template <typename TP> __device__ __forceinline__ float ldp(const TP *p, int i);
+template <> __device__ __forceinline__ float ldp<float>(const float *p, int i) { return __ldg(p + i); }
+template <> __device__ __forceinline__ float ldp<bf16>(const bf16 *p, int i) { return __bfloat162float(p[i]); }
+
+template <typename T, typename TP, int C>
 __global__ void __launch_bounds__(kEThreads)
-layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ gamma,
-              const float *__restrict__ beta, const T *__restrict__ pos, T *__restrict__ y,
+layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__restrict__ gamma,
+              const TP *__restrict__ beta, const T *__restrict__ pos, T *__restrict__ y,
               T *__restrict__ y2, float *__restrict__ mean_out, float *__restrict__ rstd_out,
-              long long rows, float eps) {
+              long long rows, float eps, float drop_p, unsigned long long seed) {
     constexpr int PER = C / 32;                 // channels per lane (8 for C = 256)
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
     static_assert(PER % VEC == 0, "C must be a multiple of 32 * VEC");
@@ -385,14 +407,24 @@ layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const float *_
         const int c = (i / VEC) * 32 * VEC + lane * VEC;
         float tmp[VEC];
         load_vec<T, VEC>(x + row * C + c, tmp);
-        if (res) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[i + k] = tmp[k];
+    }
+    if (drop_p > 0.f) {
+        float msk[PER];
+        dropout_scale<PER>(msk, seed, row, lane, drop_p);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) v[i] *= msk[i];
+    }
+    if (res) {
+#pragma unroll
+        for (int i = 0; i < PER; i += VEC) {
+            const int c = (i / VEC) * 32 * VEC + lane * VEC;
             float r2[VEC];
             load_vec<T, VEC>(res + row * C + c, r2);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) tmp[k] += r2[k];
+            for (int k = 0; k < VEC; ++k) v[i + k] += r2[k];
         }
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[i + k] = tmp[k];
     }
     float s = 0.f;
 #pragma unroll
@@ -412,7 +444,7 @@ layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const float *_
         float o[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
-            o[k] = (v[i + k] - mean) * rstd * __ldg(gamma + c + k) + __ldg(beta + c + k);
+            o[k] = (v[i + k] - mean) * rstd * ldp<TP>(gamma, c + k) + ldp<TP>(beta, c + k);
         store_vec<T, VEC>(y + row * C + c, o);
         if (y2) {
             float pz[VEC];
@@ -424,34 +456,46 @@ layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const float *_
     }
 }
 
-// Backward.  xin = x (+ res) is recomputed from the saved inputs; dy2 (grad of the y + pos output) is
-// added to dy.  dx is written once (it is also the residual's gradient); dgamma/dbeta accumulate
-// into fp32 buffers through one atomicAdd per channel per CTA.
-template <typename T, int C>
+// Backward.  xin = dropout(x) + res is recomputed from the saved inputs (same Philox bits); dy2 (grad
+// of the y + pos output) is added to dy.  d_sum is the gradient of the LayerNorm input: it is written to
+// dres (the residual's gradient) and, times the keep-mask, to dx.  Without dropout and with dres ==
+// nullptr only dx is written.  dgamma/dbeta accumulate into fp32 buffers, one atomicAdd per channel per CTA.
+template <typename T, typename TP, int C>
 __global__ void __launch_bounds__(kEThreads)
-layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ gamma,
+layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__restrict__ gamma,
               const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
               const T *__restrict__ dy, const T *__restrict__ dy2, T *__restrict__ dx,
-              float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows,
-              int rows_per_cta) {
+              T *__restrict__ dres, float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows,
+              int rows_per_cta, float drop_p, unsigned long long seed) {
     constexpr int PER = C / 32;
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
     __shared__ float s_dg[C], s_db[C];
     for (int i = threadIdx.x; i < C; i += kEThreads) { s_dg[i] = 0.f; s_db[i] = 0.f; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float adg[PER], adb[PER];
+    float adg[PER], adb[PER], gam[PER];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
+    for (int i = 0; i < PER; ++i) {
+        adg[i] = 0.f; adb[i] = 0.f;
+        gam[i] = ldp<TP>(gamma, (i / VEC) * 32 * VEC + lane * VEC + (i % VEC));
+    }
     const long long row0 = (long long)blockIdx.x * rows_per_cta;
     for (long long row = row0 + warp; row < row0 + rows_per_cta && row < rows; row += kEThreads / 32) {
         const float mean = mean_in[row], rstd = rstd_in[row];
-        float xh[PER], g[PER];
+        float xh[PER], g[PER], msk[PER];
+        if (drop_p > 0.f) {
+            dropout_scale<PER>(msk, seed, row, lane, drop_p);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) msk[i] = 1.f;
+        }
 #pragma unroll
         for (int i = 0; i < PER; i += VEC) {
             const int c = (i / VEC) * 32 * VEC + lane * VEC;
             float tx[VEC], tg[VEC];
             load_vec<T, VEC>(x + row * C + c, tx);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) tx[k] *= msk[i + k];
             if (res) {
                 float r2[VEC];
                 load_vec<T, VEC>(res + row * C + c, r2);
@@ -471,8 +515,7 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const float *_
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const int c = (i / VEC) * 32 * VEC + lane * VEC + (i % VEC);
-            const float gg = g[i] * __ldg(gamma + c);
+            const float gg = g[i] * gam[i];
             s1 += gg; s2 += gg * xh[i];
             adg[i] += g[i] * xh[i]; adb[i] += g[i];
         }
@@ -480,11 +523,14 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const float *_
 #pragma unroll
         for (int i = 0; i < PER; i += VEC) {
             const int c = (i / VEC) * 32 * VEC + lane * VEC;
-            float o[VEC];
+            float o[VEC], om[VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                o[k] = rstd * (g[i + k] * __ldg(gamma + c + k) - s1 - xh[i + k] * s2);
-            store_vec<T, VEC>(dx + row * C + c, o);
+            for (int k = 0; k < VEC; ++k) {
+                o[k] = rstd * (g[i + k] * gam[i + k] - s1 - xh[i + k] * s2);
+                om[k] = o[k] * msk[i + k];
+            }
+            store_vec<T, VEC>(dx + row * C + c, om);
+            if (dres) store_vec<T, VEC>(dres + row * C + c, o);
         }
     }
 #pragma unroll
@@ -782,62 +828,84 @@ extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
     return check_launch(who);
 }
 
-template <typename T>
-static int ln_fwd_t(const char *who, const void *x, const void *res, const float *gamma,
-                    const float *beta, const void *pos, void *y, void *y2, float *mean, float *rstd,
-                    long long rows, int C, float eps, cudaStream_t st) {
+template <typename T, typename TP>
+static int ln_fwd_t(const char *who, const void *x, const void *res, const void *gamma, const void *beta,
+                    const void *pos, void *y, void *y2, float *mean, float *rstd, long long rows, int C,
+                    float eps, float drop_p, unsigned long long seed, cudaStream_t st) {
     const unsigned grid = blocks_for(rows, kEThreads / 32);
     if (C == 256)
-        layernorm_fwd<T, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps);
+        layernorm_fwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed);
     else if (C == 512)
-        layernorm_fwd<T, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps);
+        layernorm_fwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed);
     else
         return fail("%s: embed_dims must be 256 or 512", who);
     return check_launch(who);
 }
 
-extern "C" int bevf_layernorm_forward(const void *x, const void *residual, const float *gamma,
-                                      const float *beta, const void *pos, void *y, void *y_plus_pos,
-                                      float *mean, float *rstd, int64_t rows, int C, float eps,
-                                      int dtype, void *stream) {
+extern "C" int bevf_layernorm_forward(const void *x, const void *residual, const void *gamma,
+                                      const void *beta, int param_dtype, const void *pos, void *y,
+                                      void *y_plus_pos, float *mean, float *rstd, int64_t rows, int C,
+                                      float eps, float drop_p, uint64_t seed, int dtype, void *stream) {
     const char *who = "bevf_layernorm_forward";
     BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
     if (rows == 0) return 0;
     BEVF_REQUIRE(x && gamma && beta && y, who, "null pointer argument");
     BEVF_REQUIRE((y_plus_pos == nullptr) == (pos == nullptr), who, "pos and y_plus_pos go together");
-    if (dtype == BEVF_DTYPE_F32) return ln_fwd_t<float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, (cudaStream_t)stream);
-    if (dtype == BEVF_DTYPE_BF16) return ln_fwd_t<bf16>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, (cudaStream_t)stream);
+    BEVF_REQUIRE(drop_p >= 0.f && drop_p < 1.f, who, "dropout probability must be in [0, 1)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool pb = param_dtype == BEVF_DTYPE_BF16;
+    BEVF_REQUIRE(pb || param_dtype == BEVF_DTYPE_F32, who, "unsupported parameter dtype code");
+    if (dtype == BEVF_DTYPE_F32) {
+        if (pb) return fail("%s: bf16 parameters with fp32 activations are not supported", who);
+        return ln_fwd_t<float, float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, st);
+    }
+    if (dtype == BEVF_DTYPE_BF16) {
+        if (pb) return ln_fwd_t<bf16, bf16>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, st);
+        return ln_fwd_t<bf16, float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, st);
+    }
     return fail("%s: unsupported dtype code", who);
 }
 
-template <typename T>
-static int ln_bwd_t(const char *who, const void *x, const void *res, const float *gamma,
-                    const float *mean, const float *rstd, const void *dy, const void *dy2, void *dx,
-                    float *dgamma, float *dbeta, long long rows, int C, cudaStream_t st) {
+template <typename T, typename TP>
+static int ln_bwd_t(const char *who, const void *x, const void *res, const void *gamma, const float *mean,
+                    const float *rstd, const void *dy, const void *dy2, void *dx, void *dres, float *dgamma,
+                    float *dbeta, long long rows, int C, float drop_p, unsigned long long seed,
+                    cudaStream_t st) {
     // ~4 CTAs per SM worth of row chunks keeps the per-channel atomics few
     int rows_per_cta = (int)((rows + 148 * 4 - 1) / (148 * 4));
     rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
     if (rows_per_cta < 8) rows_per_cta = 8;
     const unsigned grid = blocks_for(rows, rows_per_cta);
     if (C == 256)
-        layernorm_bwd<T, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, dgamma, dbeta, rows, rows_per_cta);
+        layernorm_bwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed);
     else if (C == 512)
-        layernorm_bwd<T, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, dgamma, dbeta, rows, rows_per_cta);
+        layernorm_bwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed);
     else
         return fail("%s: embed_dims must be 256 or 512", who);
     return check_launch(who);
 }
 
-extern "C" int bevf_layernorm_backward(const void *x, const void *residual, const float *gamma,
-                                       const float *mean, const float *rstd, const void *dy,
-                                       const void *dy_plus_pos, void *dx, float *dgamma,
-                                       float *dbeta, int64_t rows, int C, int dtype, void *stream) {
+extern "C" int bevf_layernorm_backward(const void *x, const void *residual, const void *gamma,
+                                       int param_dtype, const float *mean, const float *rstd,
+                                       const void *dy, const void *dy_plus_pos, void *dx, void *dres,
+                                       float *dgamma, float *dbeta, int64_t rows, int C, float drop_p,
+                                       uint64_t seed, int dtype, void *stream) {
     const char *who = "bevf_layernorm_backward";
     BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
     if (rows == 0) return 0;
     BEVF_REQUIRE(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, who, "null pointer argument");
-    if (dtype == BEVF_DTYPE_F32) return ln_bwd_t<float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dgamma, dbeta, rows, C, (cudaStream_t)stream);
-    if (dtype == BEVF_DTYPE_BF16) return ln_bwd_t<bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dgamma, dbeta, rows, C, (cudaStream_t)stream);
+    BEVF_REQUIRE(drop_p == 0.f || dres != nullptr || residual == nullptr, who, "dropout with a residual needs a separate dres buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool pb = param_dtype == BEVF_DTYPE_BF16;
+    BEVF_REQUIRE(pb || param_dtype == BEVF_DTYPE_F32, who, "unsupported parameter dtype code");
+    if (dtype == BEVF_DTYPE_F32) {
+        if (pb) return fail("%s: bf16 parameters with fp32 activations are not supported", who);
+        return ln_bwd_t<float, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, st);
+    }
+    if (dtype == BEVF_DTYPE_BF16) {
+        if (pb) return ln_bwd_t<bf16, bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, st);
+        return ln_bwd_t<bf16, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, st);
+    }
     return fail("%s: unsupported dtype code", who);
 }
 

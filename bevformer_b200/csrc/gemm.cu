@@ -119,7 +119,8 @@ struct GemmParams {
     int BN;                // output-tile width (multiple of 16, <= 256, divides N)
     int stages;            // smem ring depth
     int relu;
-    const float *bias;     // (N) or null
+    const void *bias;      // (N) f32 or bf16, or null
+    int bias_bf16;
     const bf16 *residual;  // (M, N) or null
     void *y;               // (M, N) bf16 or fp32
 };
@@ -225,10 +226,18 @@ gemm_nt_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
                 if (p.bias) {
+                    if (p.bias_bf16) {
+                        const uint4 *bp = reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(p.bias) + col);
+                        const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+                        const uint32_t u[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + col + i));
-                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                        for (int i = 0; i < 8; ++i) { v[2 * i] += bf16_lo(u[i]); v[2 * i + 1] += bf16_hi(u[i]); }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.bias) + col + i));
+                            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                        }
                     }
                 }
                 if (p.relu) {
@@ -453,8 +462,9 @@ static int pick_bn(int N) {
 
 using namespace bevf;
 
-extern "C" int bevf_linear_forward(const void *x, const void *w, const float *bias, const void *residual,
-                                   void *y, int y_dtype, int64_t M, int N, int K, int relu, void *stream) {
+extern "C" int bevf_linear_forward(const void *x, const void *w, const void *bias, int bias_dtype,
+                                   const void *residual, void *y, int y_dtype, int64_t M, int N, int K,
+                                   int relu, void *stream) {
     const char *who = "bevf_linear_forward";
     if (M < 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
     if (M == 0) return 0;
@@ -466,6 +476,8 @@ extern "C" int bevf_linear_forward(const void *x, const void *w, const float *bi
         (residual && !aligned16(residual)))
         return fail("%s: pointers must be 16-byte aligned", who);
     if (y_dtype != BEVF_DTYPE_BF16 && y_dtype != BEVF_DTYPE_F32) return fail("%s: unsupported dtype code", who);
+    if (bias && bias_dtype != BEVF_DTYPE_BF16 && bias_dtype != BEVF_DTYPE_F32)
+        return fail("%s: unsupported bias dtype code", who);
     const int bn = pick_bn(N);
     if (bn == 0) return fail("%s: no tile width divides N", who);
 
@@ -477,7 +489,8 @@ extern "C" int bevf_linear_forward(const void *x, const void *w, const float *bi
 
     GemmParams p;
     p.M = (int)M; p.N = N; p.K = K; p.BN = bn; p.relu = relu;
-    p.bias = bias; p.residual = reinterpret_cast<const bf16 *>(residual); p.y = y;
+    p.bias = bias; p.bias_bf16 = bias_dtype == BEVF_DTYPE_BF16;
+    p.residual = reinterpret_cast<const bf16 *>(residual); p.y = y;
     const int stage_bytes = (kBM + bn) * 128;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;

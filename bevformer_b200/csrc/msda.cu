@@ -79,6 +79,24 @@ __device__ __forceinline__ void load_levels(const int64_t *level_hw, const int64
     __syncthreads();
 }
 
+// Per-level tables for the fast kernels: element offset of the level's first pixel row (times the
+// pixel stride) and element stride between image rows, so the inner loop does no multiplies.
+struct LevelTab {
+    int h[kMaxLevels], w[kMaxLevels], rs[kMaxLevels];
+    long long lofs[kMaxLevels];
+};
+__device__ __forceinline__ void load_level_tab(const int64_t *level_hw, const int64_t *level_start, int L,
+                                               int pix, LevelTab &t) {
+    if ((int)threadIdx.x < L) {
+        const int l = threadIdx.x;
+        t.h[l] = (int)level_hw[2 * l];
+        t.w[l] = (int)level_hw[2 * l + 1];
+        t.rs[l] = t.w[l] * pix;
+        t.lofs[l] = (long long)level_start[l] * pix;
+    }
+    __syncthreads();
+}
+
 // ---- per-storage-type math ---------------------------------------------------------------------
 __device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
     float d;
@@ -168,8 +186,8 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              int iters, long long rows) {
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
     constexpr bool kHalf = (VEC == 8);
-    __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
-    load_levels(level_hw, level_start, L, s_h, s_w, s_start);
+    __shared__ LevelTab tab;
+    load_level_tab(level_hw, level_start, L, M * 32, tab);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
@@ -202,7 +220,7 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             const int l = level_of(sm, magic);
             const float2 xy = __ldg(locp + sm);
             const float a = __ldg(attp + sm);
-            const Corner c = make_corner(xy.x, xy.y, s_h[l], s_w[l]);
+            const Corner c = make_corner(xy.x, xy.y, tab.h[l], tab.w[l]);
             enc = (c.pidx * pix) | c.dx | (c.dy << 1);
             valid = c.valid;
             w00 = c.w00 * a; w01 = c.w01 * a; w10 = c.w10 * a; w11 = c.w11 * a;
@@ -216,13 +234,14 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             if (s0 + j >= LP) break;                                   // warp-uniform
             if (!(vm & (GroupMask<LANES>::kBits << j))) continue;      // nobody needs it (uniform)
             const int src = grp * LANES + j;
-            const int e = __shfl_sync(0xffffffffu, enc, src);
+            const unsigned e = (unsigned)__shfl_sync(0xffffffffu, enc, src);
             const int l = level_of(s0 + j, magic);
-            const int rs = s_w[l] * pix;
-            const T *p00 = vbase + (long long)s_start[l] * pix + (e & ~3);
-            const int ox = (e & 1) ? pix : 0, oy = (e & 2) ? rs : 0;
+            const T *vl = vbase + tab.lofs[l];                        // one 64-bit add per sample
+            const unsigned o00 = e & ~3u;
+            const unsigned o01 = o00 + ((e & 1u) ? (unsigned)pix : 0u);
+            const unsigned oy = (e & 2u) ? (unsigned)tab.rs[l] : 0u;
             Vec<T> v00, v01, v10, v11;
-            v00.load(p00); v01.load(p00 + ox); v10.load(p00 + oy); v11.load(p00 + oy + ox);
+            v00.load(vl + o00); v01.load(vl + o01); v10.load(vl + (o00 + oy)); v11.load(vl + (o01 + oy));
             if constexpr (kHalf) {
                 const uint32_t qa = __shfl_sync(0xffffffffu, wa, src);
                 const uint32_t qb = __shfl_sync(0xffffffffu, wb, src);
@@ -256,8 +275,8 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              int L, int P, int magic, int iters, long long rows) {
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
     constexpr bool kHalfDot = (VEC == 8) && (sizeof(TG) == 2);
-    __shared__ int s_h[kMaxLevels], s_w[kMaxLevels], s_start[kMaxLevels];
-    load_levels(level_hw, level_start, L, s_h, s_w, s_start);
+    __shared__ LevelTab tab;
+    load_level_tab(level_hw, level_start, L, M * 32, tab);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
@@ -304,7 +323,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
         const bool mine = sm < LP && live;
         if (mine) {
             const int l = level_of(sm, magic);
-            Hm = s_h[l]; Wm = s_w[l];
+            Hm = tab.h[l]; Wm = tab.w[l];
             const float2 xy = __ldg(locp + sm);
             a = __ldg(attp + sm);
             c = make_corner(xy.x, xy.y, Hm, Wm);
@@ -328,12 +347,11 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             const float q10 = __shfl_sync(0xffffffffu, wa10, src);
             const float q11 = __shfl_sync(0xffffffffu, wa11, src);
             const int l = level_of(s0 + j, magic);
-            const int rs = s_w[l] * pix;
-            const long long o00 = voff + (long long)s_start[l] * pix + (e & ~3);
-            const int ox = (e & 1) ? pix : 0, oy = (e & 2) ? rs : 0;
+            const long long o00 = voff + tab.lofs[l] + (long long)((unsigned)e & ~3u);
+            const int ox = (e & 1) ? pix : 0, oy = (e & 2) ? tab.rs[l] : 0;
+            const T *vp = value + o00;
             Vec<T> v00, v01, v10, v11;
-            v00.load(value + o00); v01.load(value + o00 + ox);
-            v10.load(value + o00 + oy); v11.load(value + o00 + oy + ox);
+            v00.load(vp); v01.load(vp + ox); v10.load(vp + oy); v11.load(vp + (oy + ox));
             if constexpr (kHalfDot) {
                 d[j][0] = v00.dot_h(gh); d[j][1] = v01.dot_h(gh);
                 d[j][2] = v10.dot_h(gh); d[j][3] = v11.dot_h(gh);

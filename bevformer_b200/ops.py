@@ -341,53 +341,75 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+_seed_counter = [0]
+
+
+def _next_seed() -> int:
+    """A fresh 63-bit Philox key per dropout site, derived from torch's global seed (so
+    torch.manual_seed makes runs repeatable) without touching the device."""
+    _seed_counter[0] += 1
+    return (torch.initial_seed() * 6364136223846793005 + _seed_counter[0] * 1442695040888963407) & ((1 << 63) - 1)
+
+
+def _param_ptr(p, act_dtype):
+    """Parameters are read in their own dtype when the kernel supports the combination."""
+    if p.dtype == act_dtype or p.dtype == torch.float32:
+        q = p.detach().contiguous()
+    else:
+        q = p.detach().float().contiguous()
+    return q, _DT[q.dtype]
+
+
 class LayerNormResidual(Function):
-    """y = LayerNorm(x + residual) * gamma + beta (fp32 statistics); residual may be None."""
+    """y = LayerNorm(dropout_p(x) + residual) * gamma + beta (fp32 statistics); residual may be None.
+    The dropout keep-mask is regenerated from a Philox seed in backward (nothing stored)."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, eps):
+    def forward(ctx, x, residual, gamma, beta, eps, drop_p=0.0):
         _need_cuda(x, "x")
         if x.dtype not in _DT:
             raise RuntimeError("layernorm: float32 or bfloat16 only")
         C = x.shape[-1]
         rows = x.numel() // C
-        xc = x
         rc = None if residual is None else residual.contiguous()
-        g32 = gamma.detach().float().contiguous()
-        b32 = beta.detach().float().contiguous()
-        y = torch.empty_like(xc)
+        g, pd = _param_ptr(gamma, x.dtype)
+        b, pd2 = _param_ptr(beta, x.dtype)
+        if pd != pd2:
+            g, b, pd = g.float(), b.float(), F32
+        y = torch.empty_like(x)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        seed = _next_seed() if drop_p > 0.0 else 0
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            st = lib.bevf_layernorm_forward(xc.data_ptr(), _ptr(rc), g32.data_ptr(), b32.data_ptr(),
-                                            0, y.data_ptr(), 0, mean.data_ptr(), rstd.data_ptr(),
-                                            rows, C, float(eps), _DT[x.dtype], _stream_ptr(x))
+            st = lib.bevf_layernorm_forward(x.data_ptr(), _ptr(rc), g.data_ptr(), b.data_ptr(), pd, 0,
+                                            y.data_ptr(), 0, mean.data_ptr(), rstd.data_ptr(), rows, C,
+                                            float(eps), float(drop_p), seed, _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
-        ctx.save_for_backward(xc, rc, g32, mean, rstd)
-        ctx.has_res = residual is not None
-        ctx.param_dtypes = (gamma.dtype, beta.dtype)
+        ctx.save_for_backward(x, rc, g, mean, rstd)
+        ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, res, g32, mean, rstd = ctx.saved_tensors
+        x, res, g, mean, rstd = ctx.saved_tensors
+        has_res, gdt, bdt, pd, drop_p, seed = ctx.meta
         C = x.shape[-1]
         rows = x.numel() // C
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dgamma = torch.zeros(C, device=x.device, dtype=torch.float32)
-        dbeta = torch.zeros(C, device=x.device, dtype=torch.float32)
+        dres = torch.empty_like(x) if (has_res and drop_p > 0.0) else None
+        dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            st = lib.bevf_layernorm_backward(x.data_ptr(), _ptr(res), g32.data_ptr(),
-                                             mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(), 0,
-                                             dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                             rows, C, _DT[x.dtype], _stream_ptr(x))
+            st = lib.bevf_layernorm_backward(x.data_ptr(), _ptr(res), g.data_ptr(), pd, mean.data_ptr(),
+                                             rstd.data_ptr(), dy.data_ptr(), 0, dx.data_ptr(), _ptr(dres),
+                                             dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C, drop_p, seed,
+                                             _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
-        return (dx, dx if ctx.has_res else None, dgamma.to(ctx.param_dtypes[0]),
-                dbeta.to(ctx.param_dtypes[1]), None)
+        d_res = None if not has_res else (dres if dres is not None else dx)
+        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None
 
 
 class ScaCombine(Function):
@@ -457,13 +479,13 @@ def linear_tc(x, weight, bias=None, residual=None, relu=False, out_dtype=None):
     N = weight.shape[0]
     M = x.numel() // K
     w = weight.contiguous()
-    b32 = None if bias is None else bias.detach().float().contiguous()
+    bq, bdt = (None, F32) if bias is None else _param_ptr(bias, torch.bfloat16)
     res = None if residual is None else residual.contiguous()
     out_dtype = out_dtype or torch.bfloat16
     y = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=out_dtype)
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        st = lib.bevf_linear_forward(x.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(res), y.data_ptr(),
+        st = lib.bevf_linear_forward(x.data_ptr(), w.data_ptr(), _ptr(bq), bdt, _ptr(res), y.data_ptr(),
                                      _DT[out_dtype], M, N, K, int(bool(relu)), _stream_ptr(x))
     _lib.check(st, lib)
     return y

@@ -81,9 +81,11 @@ class FFN(nn.Module):
 _register(FEEDFORWARD_NETWORK, FFN, name="FFN")
 
 
-def _fused_norm(norm: nn.LayerNorm, x, residual):
-    """LayerNorm(x + residual) in one kernel (fp32 statistics)."""
-    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps)
+def _fused_norm(norm: nn.LayerNorm, x, residual, dropout: Optional[nn.Dropout] = None):
+    """LayerNorm(dropout(x) + residual) in one kernel (fp32 statistics; the dropout of the block
+    that produced x is applied inside, active only in training mode)."""
+    p = dropout.p if (dropout is not None and dropout.training) else 0.0
+    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps, p)
 
 
 class MyCustomBaseTransformerLayer(nn.Module):
@@ -222,7 +224,7 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                 if fuse and isinstance(att, TemporalSelfAttention) and att.batch_first:
                     pre = att.attend(query, prev_bev, bev_pos, query_key_padding_mask, ref_2d,
                                      tsa_ss, tsa_lsi)
-                    query = _fused_norm(self.norms[ni], att.dropout(pre), query)
+                    query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1
                 else:
@@ -238,7 +240,7 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                     pre = att.attend(query, value if value is not None else key, reference_points_cam,
                                      kwargs.get("bev_mask"), spatial_shapes, level_start_index,
                                      kwargs.get("sca_plan"))
-                    query = _fused_norm(self.norms[ni], att.dropout(pre), query)
+                    query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1
                 else:
@@ -253,8 +255,8 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
             elif op == "ffn":
                 ffn = self.ffns[fi]
                 if fuse and isinstance(ffn, FFN) and ffn.add_identity:
-                    pre = ffn.layers[ffn.num_fcs](ffn.transform(query))
-                    query = _fused_norm(self.norms[ni], pre, query)
+                    query = _fused_norm(self.norms[ni], ffn.transform(query), query,
+                                        ffn.layers[ffn.num_fcs])
                     ni += 1
                     i += 1
                 else:

@@ -163,24 +163,29 @@ BEVF_API int bevf_tsa_prep_backward(const float *raw, const float *grad_loc, con
                                     int L, int P, void *stream);
 
 /*
- * y = LayerNorm(x + residual) * gamma + beta, optionally also y_plus_pos = y + pos.
+ * y = LayerNorm(dropout(x) + residual) * gamma + beta, optionally also y_plus_pos = y + pos.
  * replaces the `norm` steps of BEVFormerLayer.forward (encoder.py:377-379) together with the
- * preceding "+ identity" of the attention / FFN (temporal_self_attention.py:272,
- * spatial_cross_attention.py:175, mmcv FFN) and TSA's `query + query_pos`
- * (temporal_self_attention.py:186-187).  residual / pos / y_plus_pos / mean / rstd may be NULL.
- * x, residual, pos, y, y_plus_pos: (rows, C) in `dtype`; gamma, beta, mean, rstd: f32. C in {256,512}.
+ * preceding "self.dropout(output) + identity" of the attention / FFN
+ * (temporal_self_attention.py:272, spatial_cross_attention.py:175, mmcv FFN) and TSA's
+ * `query + query_pos` (temporal_self_attention.py:186-187).
+ *   x, residual, pos, y, y_plus_pos: (rows, C) in `dtype`; gamma, beta: (C) in `param_dtype`;
+ *   mean, rstd: (rows) f32.  residual / pos / y_plus_pos / mean / rstd may be NULL.  C in {256, 512}.
+ *   drop_p in [0,1): inverted dropout on x with keep-mask bits from Philox4x32-10(seed, row*32+lane);
+ *   the backward regenerates the same bits from `seed`, no mask tensor exists.  drop_p = 0: no dropout.
  */
-BEVF_API int bevf_layernorm_forward(const void *x, const void *residual, const float *gamma,
-                                    const float *beta, const void *pos, void *y, void *y_plus_pos,
-                                    float *mean, float *rstd, int64_t rows, int C, float eps,
-                                    int dtype, void *stream);
+BEVF_API int bevf_layernorm_forward(const void *x, const void *residual, const void *gamma,
+                                    const void *beta, int param_dtype, const void *pos, void *y,
+                                    void *y_plus_pos, float *mean, float *rstd, int64_t rows, int C,
+                                    float eps, float drop_p, uint64_t seed, int dtype, void *stream);
 
-/* dx (rows, C) is fully overwritten (it is also d residual); dgamma / dbeta (C,) f32 are
- * ACCUMULATED INTO.  dy_plus_pos may be NULL. */
-BEVF_API int bevf_layernorm_backward(const void *x, const void *residual, const float *gamma,
-                                     const float *mean, const float *rstd, const void *dy,
-                                     const void *dy_plus_pos, void *dx, float *dgamma, float *dbeta,
-                                     int64_t rows, int C, int dtype, void *stream);
+/* dx (rows, C) = gradient of x, fully overwritten; dres = gradient of residual (may be NULL when
+ * drop_p == 0: it then equals dx); dgamma / dbeta (C,) f32 are ACCUMULATED INTO.  dy_plus_pos may be
+ * NULL.  drop_p / seed must be the forward call's. */
+BEVF_API int bevf_layernorm_backward(const void *x, const void *residual, const void *gamma,
+                                     int param_dtype, const float *mean, const float *rstd,
+                                     const void *dy, const void *dy_plus_pos, void *dx, void *dres,
+                                     float *dgamma, float *dbeta, int64_t rows, int C, float drop_p,
+                                     uint64_t seed, int dtype, void *stream);
 
 /*
  * slots[b,q,:] = inv_count[b,q] * sum_{cameras seeing q} out[b*R + pair_of[cam][q], :]
@@ -211,13 +216,14 @@ BEVF_API int bevf_point_sampling(const float *lidar2img, const float *pc_range, 
  * replaces nn.Linear (cuBLAS GEMM + bias) and the ReLU / "+ identity" launches that follow it in
  * TemporalSelfAttention (temporal_self_attention.py:198,206-209,267), MSDeformableAttention3D /
  * SpatialCrossAttention (spatial_cross_attention.py:334,338-341,173) and mmcv's FFN.
- *   x (M,K) bf16, w (N,K) bf16 (nn.Linear layout), bias (N) f32 or NULL, residual (M,N) bf16 or NULL,
+ *   x (M,K) bf16, w (N,K) bf16 (nn.Linear layout), bias (N) in bias_dtype (f32 | bf16) or NULL,
+ *   residual (M,N) bf16 or NULL,
  *   y (M,N) in y_dtype (bf16 | f32, straight from the fp32 accumulator).  relu != 0 applies
  *   max(.,0) before the residual add.  K % 64 == 0, N % 16 == 0.
  */
-BEVF_API int bevf_linear_forward(const void *x, const void *w, const float *bias, const void *residual,
-                                 void *y, int y_dtype, int64_t M, int N, int K, int relu,
-                                 void *stream);
+BEVF_API int bevf_linear_forward(const void *x, const void *w, const void *bias, int bias_dtype,
+                                 const void *residual, void *y, int y_dtype, int64_t M, int N, int K,
+                                 int relu, void *stream);
 
 /*
  * Weight gradient of the projection above:  dw[N,K] += dy[M,N]^T . x[M,K]   (fp32, ACCUMULATED

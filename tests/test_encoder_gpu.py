@@ -212,3 +212,38 @@ def test_prep_and_reduction_kernels_against_torch():
     assert rel_err(ops.colsum(x), x.double().sum(0)) < 1e-5
     xb = x.bfloat16()
     assert rel_err(ops.colsum(xb), xb.double().sum(0)) < 1e-5
+
+
+def test_fused_dropout_layernorm_is_consistent():
+    """The keep-mask is never stored: backward regenerates it from the Philox seed.  dx is exactly 0
+    where an element was dropped, which reveals the mask; the forward output must equal a LayerNorm
+    of the input scaled by that mask, and the drop rate must match p."""
+    from bevformer_b200 import ops
+    torch.manual_seed(123)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        x = torch.randn(5000, 256, device=DEV).to(dtype).requires_grad_(True)
+        res = torch.randn(5000, 256, device=DEV).to(dtype).requires_grad_(True)
+        gamma = (1 + 0.1 * torch.randn(256, device=DEV)).to(dtype).requires_grad_(True)
+        beta = (0.1 * torch.randn(256, device=DEV)).to(dtype).requires_grad_(True)
+        p = 0.3
+        y = ops.LayerNormResidual.apply(x, res, gamma, beta, 1e-5, p)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        keep = (x.grad != 0)
+        rate = 1.0 - keep.float().mean().item()
+        assert abs(rate - p) < 0.01, rate
+        xs = x.detach().float() * keep / (1 - p) + res.detach().float()
+        ref = torch.nn.functional.layer_norm(xs, (256,), gamma.detach().float(), beta.detach().float(), 1e-5)
+        assert rel_err(y.float(), ref) < tol
+        # gradient of the residual branch is the unmasked LayerNorm gradient
+        xs2 = xs.clone().requires_grad_(True)
+        torch.nn.functional.layer_norm(xs2, (256,), gamma.detach().float(), beta.detach().float(), 1e-5).backward(dy.float())
+        assert rel_err(res.grad.float(), xs2.grad) < tol
+        assert rel_err(x.grad.float(), xs2.grad * keep / (1 - p)) < tol
+        # p = 0 reproduces plain residual LayerNorm and two calls draw different masks
+        y0 = ops.LayerNormResidual.apply(x.detach(), res.detach(), gamma.detach(), beta.detach(), 1e-5, 0.0)
+        ref0 = torch.nn.functional.layer_norm(x.detach().float() + res.detach().float(), (256,),
+                                              gamma.detach().float(), beta.detach().float(), 1e-5)
+        assert rel_err(y0.float(), ref0) < tol
+        y_again = ops.LayerNormResidual.apply(x.detach(), res.detach(), gamma.detach(), beta.detach(), 1e-5, p)
+        assert not torch.equal(y_again, y.detach())

@@ -21,6 +21,8 @@
 // is sized for full-width rows (BN up to 256) rather than for tensor-pipe peak.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bevf {
@@ -283,6 +285,233 @@ gemm_nt_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 }
 
 
+
+// ================================================================================================
+// v2 of the NT projection: weight-stationary.
+//
+// ncu on v1 (profiles/README.md): tensor pipe 15 % active, DRAM 13 %, 8 resident warps idle -- every
+// 128 x BN output tile re-fetched its BN x K weight tile (128 KB) from L2, and one SM's share of L2
+// bandwidth is only ~42 B/clk.  Here each CTA loads the weight tile of the current column block ONCE
+// into shared memory (<= 128 KB, SWIZZLE_128B k-blocks) and streams only the activation rows past it:
+//   warp 0     TMA producer: B once per column block, then A k-blocks (128 x 64) through a ring
+//   warp 1     MMA issuer: tcgen05.mma with the A descriptor of the ring stage and the B descriptor of
+//              the resident k-block; accumulators double-buffered in TMEM
+//   warps 4-7  epilogue: tcgen05.ld 64 (bf16 out) / 32 (fp32 out) columns at a time, bias from shared
+//              memory, ReLU, convert, write a 32-row x 128 B slab into a SWIZZLE_128B staging buffer
+//              and hand it to the TMA store engine (cp.async.bulk.tensor ... global <- shared): the
+//              threads issue no global stores, rows beyond M are clipped by the tensor map.
+// ================================================================================================
+struct GemmWsParams {
+    int M, N, K;
+    int BN;                // column block (multiple of 16, <= 256, BN * K * 2 <= 128 KB, divides N)
+    int stages;            // A ring depth
+    int relu;
+    const void *bias;      // (N) f32 or bf16, or null
+    int bias_bf16;
+    int out_f32;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_y, const GemmWsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kblocks = p.K / kBK;
+    const int b_kb_bytes = p.BN * 128;                    // one resident k-block of the weight tile
+    const int b_bytes = kblocks * b_kb_bytes;             // <= 128 KB, multiple of 2 KB
+    const int a_bytes = kBM * 128;
+    uint8_t *smem_b = smem;
+    uint8_t *smem_a = smem_b + ((b_bytes + 1023) & ~1023);
+    uint8_t *smem_c = smem_a + (size_t)p.stages * a_bytes;           // 4 warps x 2 buffers x 4 KB
+    float *s_bias = reinterpret_cast<float *>(smem_c + 4 * 2 * 4096);  // BN floats (<= 1 KB)
+    uint64_t *full = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_bias) + 1024);
+    uint64_t *empty = full + p.stages;
+    uint64_t *acc_full = empty + p.stages;
+    uint64_t *acc_empty = acc_full + kAccStages;
+    uint64_t *b_full = acc_empty + kAccStages;
+    uint64_t *b_empty = b_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + kBM - 1) / kBM, tiles_n = p.N / p.BN;
+    const uint32_t tmem_cols = (kAccStages * p.BN <= 32) ? 32 : (kAccStages * p.BN <= 64) ? 64
+                             : (kAccStages * p.BN <= 128) ? 128 : (kAccStages * p.BN <= 256) ? 256 : 512;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(b_full, 1);
+        mbar_init(b_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int tn = 0; tn < tiles_n; ++tn) {
+                mbar_wait(b_empty, (uint32_t)((tn & 1) ^ 1));         // previous column block fully consumed
+                mbar_expect_tx(b_full, (uint32_t)b_bytes);
+                for (int kb = 0; kb < kblocks; ++kb)
+                    tma_load_2d(smem_b + (size_t)kb * b_kb_bytes, &map_b, b_full, kb * kBK, tn * p.BN);
+                for (int tm = blockIdx.x; tm < tiles_m; tm += gridDim.x) {
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], (uint32_t)a_bytes);
+                        tma_load_2d(smem_a + (size_t)s * a_bytes, &map_a, &full[s], kb * kBK, tm * kBM);
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16(kBM, p.BN);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (int tn = 0; tn < tiles_n; ++tn) {
+                mbar_wait(b_full, (uint32_t)(tn & 1));
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(smem_b);
+                for (int tm = blockIdx.x; tm < tiles_m; tm += gridDim.x) {
+                    mbar_wait(&acc_empty[as], aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        const uint64_t da = smem_desc_k_sw128(smem_u32(smem_a + (size_t)s * a_bytes));
+                        const uint64_t db = smem_desc_k_sw128(b_addr + (uint32_t)(kb * b_kb_bytes));
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                      (uint32_t)((kb | k) != 0));
+                        umma_commit(&empty[s]);
+                        if (kb == kblocks - 1) umma_commit(&acc_full[as]);
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
+                    }
+                    if (++as == kAccStages) { as = 0; aph ^= 1; }
+                }
+                umma_commit(b_empty);                      // all MMAs reading this weight tile have retired
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int et = threadIdx.x - 128;                             // 0..127 among the epilogue threads
+        uint8_t *my_c = smem_c + (size_t)q * 2 * 4096;
+        const int cols_per_chunk = p.out_f32 ? 32 : 64;               // 128 B of output per row
+        int as = 0; uint32_t aph = 0;
+        int cbuf = 0;
+        for (int tn = 0; tn < tiles_n; ++tn) {
+            // bias of this column block -> shared memory (all 128 epilogue threads)
+            named_bar_sync(1, 128);                                    // previous block's readers are done
+            for (int i = et; i < p.BN; i += 128) {
+                float bv = 0.f;
+                if (p.bias) {
+                    const int col = tn * p.BN + i;
+                    bv = p.bias_bf16 ? __bfloat162float(reinterpret_cast<const bf16 *>(p.bias)[col])
+                                     : reinterpret_cast<const float *>(p.bias)[col];
+                }
+                s_bias[i] = bv;
+            }
+            named_bar_sync(1, 128);
+            for (int tm = blockIdx.x; tm < tiles_m; tm += gridDim.x) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN);
+                const int row0 = tm * kBM + q * 32;
+                for (int c0 = 0; c0 < p.BN; c0 += cols_per_chunk) {
+                    uint8_t *buf = my_c + (size_t)cbuf * 4096;
+                    // the TMA store that last read this buffer (two chunks ago) must have drained it
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    if (!p.out_f32) {
+                        uint32_t r[4][16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tmem_ld16(taddr + (uint32_t)(c0 + 16 * i), r[i]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {                 // eight 16 B chunks = 8 columns each
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int c = 8 * i + j;
+                                float t = __uint_as_float(r[c >> 4][c & 15]) + s_bias[c0 + c];
+                                v[j] = p.relu ? fmaxf(t, 0.f) : t;
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+                            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                            *reinterpret_cast<uint4 *>(buf + lane * 128 + ((i ^ (lane & 7)) << 4)) = o;
+                        }
+                    } else {
+                        uint32_t r[2][16];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) tmem_ld16(taddr + (uint32_t)(c0 + 16 * i), r[i]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {                 // eight 16 B chunks = 4 columns each
+                            float v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = 4 * i + j;
+                                float t = __uint_as_float(r[c >> 4][c & 15]) + s_bias[c0 + c];
+                                v[j] = p.relu ? fmaxf(t, 0.f) : t;
+                            }
+                            *reinterpret_cast<float4 *>(buf + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                                make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
+                    fence_async_smem();                               // generic-proxy writes -> async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_y, buf, tn * p.BN + c0, row0);
+                        tma_store_commit();
+                    }
+                    cbuf ^= 1;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+                if (++as == kAccStages) { as = 0; aph ^= 1; }
+            }
+        }
+        if (lane == 0) tma_store_wait_read<0>();                     // staging memory must outlive the reads
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // ================================================================================================
 // Weight gradient:  dW[N, K] += dY[M, N]^T . X[M, K]      (reduction over the M rows)
 //
@@ -451,6 +680,30 @@ static int make_map_2d(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+static int make_map_out(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, bool f32) {
+    // output (rows, cols): box = 32 rows x 128 B (64 bf16 / 32 fp32 columns), SWIZZLE_128B
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return -1;
+    const uint32_t esz = f32 ? 4 : 2;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * esz};
+    cuuint32_t box[2] = {128 / esz, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// weight-stationary tile width: the largest multiple of 16 that divides N, is <= 256, whose weight
+// tile fits 128 KB of shared memory, and (for the 128 B output slabs) is a multiple of `gran` columns
+static int pick_bn_ws(int N, int K, int gran) {
+    for (int bn = 256; bn >= 16; bn -= 16)
+        if (N % bn == 0 && bn % gran == 0 && (long long)bn * K * 2 <= 128 * 1024) return bn;
+    return 0;
+}
+
 static int pick_bn(int N) {
     for (int bn : {256, 192, 128, 64}) if (N % bn == 0) return bn;
     if (N <= 256 && N % 16 == 0) return N;
@@ -478,6 +731,42 @@ extern "C" int bevf_linear_forward(const void *x, const void *w, const void *bia
     if (y_dtype != BEVF_DTYPE_BF16 && y_dtype != BEVF_DTYPE_F32) return fail("%s: unsupported dtype code", who);
     if (bias && bias_dtype != BEVF_DTYPE_BF16 && bias_dtype != BEVF_DTYPE_F32)
         return fail("%s: unsupported bias dtype code", who);
+    static int use_ws = -1;
+    if (use_ws < 0) {
+        const char *e = getenv("BEVF_GEMM_WS");
+        use_ws = e ? atoi(e) : 1;
+    }
+    const bool f32 = y_dtype == BEVF_DTYPE_F32;
+    const int bn_ws = pick_bn_ws(N, K, f32 ? 32 : 64);
+    if (use_ws && !residual && bn_ws > 0) {
+        CUtensorMap map_a, map_b, map_y;
+        if (int e = make_map_2d(&map_a, x, (uint64_t)M, (uint64_t)K, kBM))
+            return fail("%s: cuTensorMapEncodeTiled(A) failed (%lld)", who, e);
+        if (int e = make_map_2d(&map_b, w, (uint64_t)N, (uint64_t)K, (uint32_t)bn_ws))
+            return fail("%s: cuTensorMapEncodeTiled(B) failed (%lld)", who, e);
+        if (int e = make_map_out(&map_y, y, (uint64_t)M, (uint64_t)N, f32))
+            return fail("%s: cuTensorMapEncodeTiled(Y) failed (%lld)", who, e);
+        GemmWsParams q;
+        q.M = (int)M; q.N = N; q.K = K; q.BN = bn_ws; q.relu = relu; q.bias = bias;
+        q.bias_bf16 = bias_dtype == BEVF_DTYPE_BF16; q.out_f32 = f32 ? 1 : 0;
+        const int b_bytes = ((bn_ws * K * 2) + 1023) & ~1023;
+        int stages = (227 * 1024 - 1024 - b_bytes - 32 * 1024 - 1024 - 256) / (kBM * 128);
+        if (stages > 6) stages = 6;
+        if (stages < 2) return fail("%s: not enough shared memory for the A ring", who);
+        q.stages = stages;
+        const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * kBM * 128 + 32 * 1024 + 1024 + 256;
+        static int sms_ws = 0;
+        if (sms_ws == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms_ws, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(gemm_nt_ws_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        }
+        const int tiles_m = (int)((M + kBM - 1) / kBM);
+        const int grid = tiles_m < sms_ws ? tiles_m : sms_ws;
+        gemm_nt_ws_bf16<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, q);
+        return check_launch(who);
+    }
     const int bn = pick_bn(N);
     if (bn == 0) return fail("%s: no tile width divides N", who);
 

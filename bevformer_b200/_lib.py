@@ -35,10 +35,11 @@ SIGNATURES = {
     "bevf_tsa_prep_forward": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "bevf_tsa_prep_backward": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "bevf_layernorm_forward": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 5
-                               + [c_int64, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_uint64, c_int,
-                                  c_void_p]),
+                               + [c_int64, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_uint64, c_void_p,
+                                  c_int, c_void_p]),
     "bevf_layernorm_backward": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 8
-                                + [c_int64, c_int, ctypes.c_float, ctypes.c_uint64, c_int, c_void_p]),
+                                + [c_int64, c_int, ctypes.c_float, ctypes.c_uint64, c_void_p, c_int,
+                                   c_void_p]),
     "bevf_sca_combine_forward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "bevf_sca_combine_backward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "bevf_linear_forward": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2

@@ -394,8 +394,10 @@ __global__ void __launch_bounds__(kEThreads)
 layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__restrict__ gamma,
               const TP *__restrict__ beta, const T *__restrict__ pos, T *__restrict__ y,
               T *__restrict__ y2, float *__restrict__ mean_out, float *__restrict__ rstd_out,
-              long long rows, float eps, float drop_p, unsigned long long seed) {
+              long long rows, float eps, float drop_p, unsigned long long seed,
+              const unsigned long long *__restrict__ seed_base) {
     constexpr int PER = C / 32;                 // channels per lane (8 for C = 256)
+    if (seed_base) seed += *seed_base;          // device-side step counter (CUDA-graph replays)
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
     static_assert(PER % VEC == 0, "C must be a multiple of 32 * VEC");
     const int lane = threadIdx.x & 31;
@@ -466,9 +468,11 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
               const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
               const T *__restrict__ dy, const T *__restrict__ dy2, T *__restrict__ dx,
               T *__restrict__ dres, float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows,
-              int rows_per_cta, float drop_p, unsigned long long seed) {
+              int rows_per_cta, float drop_p, unsigned long long seed,
+              const unsigned long long *__restrict__ seed_base) {
     constexpr int PER = C / 32;
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    if (seed_base) seed += *seed_base;
     __shared__ float s_dg[C], s_db[C];
     for (int i = threadIdx.x; i < C; i += kEThreads) { s_dg[i] = 0.f; s_db[i] = 0.f; }
     __syncthreads();
@@ -831,12 +835,13 @@ extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
 template <typename T, typename TP>
 static int ln_fwd_t(const char *who, const void *x, const void *res, const void *gamma, const void *beta,
                     const void *pos, void *y, void *y2, float *mean, float *rstd, long long rows, int C,
-                    float eps, float drop_p, unsigned long long seed, cudaStream_t st) {
+                    float eps, float drop_p, unsigned long long seed, const unsigned long long *sb,
+                    cudaStream_t st) {
     const unsigned grid = blocks_for(rows, kEThreads / 32);
     if (C == 256)
-        layernorm_fwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed);
+        layernorm_fwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed, sb);
     else if (C == 512)
-        layernorm_fwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed);
+        layernorm_fwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed, sb);
     else
         return fail("%s: embed_dims must be 256 or 512", who);
     return check_launch(who);
@@ -845,8 +850,10 @@ static int ln_fwd_t(const char *who, const void *x, const void *res, const void 
 extern "C" int bevf_layernorm_forward(const void *x, const void *residual, const void *gamma,
                                       const void *beta, int param_dtype, const void *pos, void *y,
                                       void *y_plus_pos, float *mean, float *rstd, int64_t rows, int C,
-                                      float eps, float drop_p, uint64_t seed, int dtype, void *stream) {
+                                      float eps, float drop_p, uint64_t seed, const uint64_t *seed_base,
+                                      int dtype, void *stream) {
     const char *who = "bevf_layernorm_forward";
+    const unsigned long long *sb = reinterpret_cast<const unsigned long long *>(seed_base);
     BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
     if (rows == 0) return 0;
     BEVF_REQUIRE(x && gamma && beta && y, who, "null pointer argument");
@@ -857,11 +864,11 @@ extern "C" int bevf_layernorm_forward(const void *x, const void *residual, const
     BEVF_REQUIRE(pb || param_dtype == BEVF_DTYPE_F32, who, "unsupported parameter dtype code");
     if (dtype == BEVF_DTYPE_F32) {
         if (pb) return fail("%s: bf16 parameters with fp32 activations are not supported", who);
-        return ln_fwd_t<float, float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, st);
+        return ln_fwd_t<float, float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, sb, st);
     }
     if (dtype == BEVF_DTYPE_BF16) {
-        if (pb) return ln_fwd_t<bf16, bf16>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, st);
-        return ln_fwd_t<bf16, float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, st);
+        if (pb) return ln_fwd_t<bf16, bf16>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, sb, st);
+        return ln_fwd_t<bf16, float>(who, x, residual, gamma, beta, pos, y, y_plus_pos, mean, rstd, rows, C, eps, drop_p, seed, sb, st);
     }
     return fail("%s: unsupported dtype code", who);
 }
@@ -870,16 +877,16 @@ template <typename T, typename TP>
 static int ln_bwd_t(const char *who, const void *x, const void *res, const void *gamma, const float *mean,
                     const float *rstd, const void *dy, const void *dy2, void *dx, void *dres, float *dgamma,
                     float *dbeta, long long rows, int C, float drop_p, unsigned long long seed,
-                    cudaStream_t st) {
+                    const unsigned long long *sb, cudaStream_t st) {
     // ~4 CTAs per SM worth of row chunks keeps the per-channel atomics few
     int rows_per_cta = (int)((rows + 148 * 4 - 1) / (148 * 4));
     rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
     if (rows_per_cta < 8) rows_per_cta = 8;
     const unsigned grid = blocks_for(rows, rows_per_cta);
     if (C == 256)
-        layernorm_bwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed);
+        layernorm_bwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed, sb);
     else if (C == 512)
-        layernorm_bwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed);
+        layernorm_bwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed, sb);
     else
         return fail("%s: embed_dims must be 256 or 512", who);
     return check_launch(who);
@@ -889,8 +896,10 @@ extern "C" int bevf_layernorm_backward(const void *x, const void *residual, cons
                                        int param_dtype, const float *mean, const float *rstd,
                                        const void *dy, const void *dy_plus_pos, void *dx, void *dres,
                                        float *dgamma, float *dbeta, int64_t rows, int C, float drop_p,
-                                       uint64_t seed, int dtype, void *stream) {
+                                       uint64_t seed, const uint64_t *seed_base, int dtype,
+                                       void *stream) {
     const char *who = "bevf_layernorm_backward";
+    const unsigned long long *sb = reinterpret_cast<const unsigned long long *>(seed_base);
     BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
     if (rows == 0) return 0;
     BEVF_REQUIRE(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, who, "null pointer argument");
@@ -900,11 +909,11 @@ extern "C" int bevf_layernorm_backward(const void *x, const void *residual, cons
     BEVF_REQUIRE(pb || param_dtype == BEVF_DTYPE_F32, who, "unsupported parameter dtype code");
     if (dtype == BEVF_DTYPE_F32) {
         if (pb) return fail("%s: bf16 parameters with fp32 activations are not supported", who);
-        return ln_bwd_t<float, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, st);
+        return ln_bwd_t<float, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, st);
     }
     if (dtype == BEVF_DTYPE_BF16) {
-        if (pb) return ln_bwd_t<bf16, bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, st);
-        return ln_bwd_t<bf16, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, st);
+        if (pb) return ln_bwd_t<bf16, bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, st);
+        return ln_bwd_t<bf16, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, st);
     }
     return fail("%s: unsupported dtype code", who);
 }

@@ -342,6 +342,20 @@ def _ptr(t):
 
 
 _seed_counter = [0]
+_seed_state: dict = {}        # device -> int64[1] step counter living on the device
+
+
+def seed_state(device) -> torch.Tensor:
+    key = torch.device(device)
+    if key not in _seed_state:
+        _seed_state[key] = torch.zeros(1, dtype=torch.int64, device=key)
+    return _seed_state[key]
+
+
+def advance_seed(device) -> None:
+    """Bump the device-side dropout step counter (one tiny kernel; capturable in a CUDA graph, so
+    every replay of a captured training step draws new masks)."""
+    seed_state(device).add_(0x9E3779B97F4A7C1)
 
 
 def _next_seed() -> int:
@@ -380,11 +394,13 @@ class LayerNormResidual(Function):
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
         seed = _next_seed() if drop_p > 0.0 else 0
+        sbase = seed_state(x.device) if drop_p > 0.0 else None
         lib = _lib.load()
         with torch.cuda.device(x.device):
             st = lib.bevf_layernorm_forward(x.data_ptr(), _ptr(rc), g.data_ptr(), b.data_ptr(), pd, 0,
                                             y.data_ptr(), 0, mean.data_ptr(), rstd.data_ptr(), rows, C,
-                                            float(eps), float(drop_p), seed, _DT[x.dtype], _stream_ptr(x))
+                                            float(eps), float(drop_p), seed, _ptr(sbase), _DT[x.dtype],
+                                            _stream_ptr(x))
         _lib.check(st, lib)
         ctx.save_for_backward(x, rc, g, mean, rstd)
         ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed)
@@ -406,6 +422,7 @@ class LayerNormResidual(Function):
             st = lib.bevf_layernorm_backward(x.data_ptr(), _ptr(res), g.data_ptr(), pd, mean.data_ptr(),
                                              rstd.data_ptr(), dy.data_ptr(), 0, dx.data_ptr(), _ptr(dres),
                                              dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C, drop_p, seed,
+                                             _ptr(seed_state(x.device)) if drop_p > 0.0 else 0,
                                              _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         d_res = None if not has_res else (dres if dres is not None else dx)

@@ -348,6 +348,27 @@ class BEVFormerEncoder(nn.Module):
         h, w = img_metas[0]["img_shape"][0][0], img_metas[0]["img_shape"][0][1]   # quirk 10
         return ops.point_sampling(l2i, self.pc_range, z_norm, h, w, bev_h, bev_w)
 
+    def prepare(self, img_metas, bev_h, bev_w, device) -> ScaPlan:
+        """Everything of a forward that depends only on the camera rig: pillar projection, in-view
+        mask, the (camera, query) pair plan.  This is the part with the host copy of lidar2img and the
+        one host sync; callers with a static rig (or a CUDA-graph-captured step) run it once and pass
+        the result as ``sca_plan=``."""
+        bs = len(img_metas)
+        ref_cam, bev_mask = self._camera_geometry(bs, bev_h, bev_w, img_metas, torch.device(device))
+        return ScaPlan.build(bev_mask, ref_cam, (bev_h, bev_w))
+
+    def _constants(self, bev_h, bev_w, bs, dev):
+        """Small device tensors that never change for a BEV size (built once: creating a tensor from
+        Python numbers is a pageable host copy, which a stream capture does not allow)."""
+        key = (bev_h, bev_w, bs, str(dev))
+        cache = self.__dict__.setdefault("_const_cache", {})
+        if key not in cache:
+            ref_2d = self.get_reference_points(bev_h, bev_w, dim="2d", bs=bs, device=dev,
+                                               dtype=torch.float32)
+            cache[key] = (ref_2d, torch.tensor([[bev_h, bev_w]], device=dev, dtype=torch.int64),
+                          torch.zeros(1, device=dev, dtype=torch.int64))
+        return cache[key]
+
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, bev_query, key, value, *args, bev_h=None, bev_w=None, bev_pos=None,
                 spatial_shapes=None, level_start_index=None, valid_ratios=None, prev_bev=None,
@@ -357,16 +378,21 @@ class BEVFormerEncoder(nn.Module):
         (same contract as encoder.py:151-239)."""
         bs = bev_query.size(1)
         dev, dtype = bev_query.device, bev_query.dtype
-        ref_2d = self.get_reference_points(bev_h, bev_w, dim="2d", bs=bs, device=dev,
-                                           dtype=torch.float32)
-        if dev.type == "cuda":
-            ref_cam, bev_mask = self._camera_geometry(bs, bev_h, bev_w, kwargs["img_metas"], dev)
-        else:
-            ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
-                                               self.num_points_in_pillar, dim="3d", bs=bs,
-                                               device=dev, dtype=dtype)
-            ref_cam, bev_mask = self.point_sampling(ref_3d, self.pc_range, kwargs["img_metas"])
-        plan = kwargs.pop("sca_plan", None) or ScaPlan.build(bev_mask, ref_cam, (bev_h, bev_w))
+        ref_2d, tsa_ss, tsa_lsi = self._constants(bev_h, bev_w, bs, dev)
+        plan = kwargs.pop("sca_plan", None)
+        bev_mask = None
+        if plan is None:
+            if dev.type == "cuda":
+                ref_cam, bev_mask = self._camera_geometry(bs, bev_h, bev_w, kwargs["img_metas"], dev)
+            else:
+                ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
+                                                   self.num_points_in_pillar, dim="3d", bs=bs,
+                                                   device=dev, dtype=dtype)
+                ref_cam, bev_mask = self.point_sampling(ref_3d, self.pc_range, kwargs["img_metas"])
+            plan = ScaPlan.build(bev_mask, ref_cam, (bev_h, bev_w))
+        ref_cam = plan.ref_cam
+        if self.training and dev.type == "cuda":
+            ops.advance_seed(dev)                 # new dropout masks this step (also under graph replay)
 
         shift = torch.as_tensor(shift, device=dev, dtype=torch.float32)
         shift_ref = ref_2d + (shift[:, None, None, :] if shift.dim() == 2 else shift)   # quirk 9
@@ -380,8 +406,6 @@ class BEVFormerEncoder(nn.Module):
             queue = None
             hybrid = torch.stack([ref_2d, ref_2d], 1).reshape(bs * 2, nq, 1, 2)
         hybrid = hybrid.contiguous()
-        tsa_ss = torch.tensor([[bev_h, bev_w]], device=dev, dtype=torch.int64)
-        tsa_lsi = torch.zeros(1, device=dev, dtype=torch.int64)
         ss = torch.as_tensor(spatial_shapes).to(device=dev, dtype=torch.int64).contiguous()
         lsi = torch.as_tensor(level_start_index).to(device=dev, dtype=torch.int64).contiguous()
 

@@ -172,11 +172,14 @@ BEVF_API int bevf_tsa_prep_backward(const float *raw, const float *grad_loc, con
  *   mean, rstd: (rows) f32.  residual / pos / y_plus_pos / mean / rstd may be NULL.  C in {256, 512}.
  *   drop_p in [0,1): inverted dropout on x with keep-mask bits from Philox4x32-10(seed, row*32+lane);
  *   the backward regenerates the same bits from `seed`, no mask tensor exists.  drop_p = 0: no dropout.
+ *   seed_base (DEVICE, may be NULL) is added to seed inside the kernel: a step counter kept on the
+ *   device lets a captured CUDA graph draw new masks on every replay.
  */
 BEVF_API int bevf_layernorm_forward(const void *x, const void *residual, const void *gamma,
                                     const void *beta, int param_dtype, const void *pos, void *y,
                                     void *y_plus_pos, float *mean, float *rstd, int64_t rows, int C,
-                                    float eps, float drop_p, uint64_t seed, int dtype, void *stream);
+                                    float eps, float drop_p, uint64_t seed, const uint64_t *seed_base,
+                                    int dtype, void *stream);
 
 /* dx (rows, C) = gradient of x, fully overwritten; dres = gradient of residual (may be NULL when
  * drop_p == 0: it then equals dx); dgamma / dbeta (C,) f32 are ACCUMULATED INTO.  dy_plus_pos may be
@@ -185,7 +188,7 @@ BEVF_API int bevf_layernorm_backward(const void *x, const void *residual, const 
                                      int param_dtype, const float *mean, const float *rstd,
                                      const void *dy, const void *dy_plus_pos, void *dx, void *dres,
                                      float *dgamma, float *dbeta, int64_t rows, int C, float drop_p,
-                                     uint64_t seed, int dtype, void *stream);
+                                     uint64_t seed, const uint64_t *seed_base, int dtype, void *stream);
 
 /*
  * slots[b,q,:] = inv_count[b,q] * sum_{cameras seeing q} out[b*R + pair_of[cam][q], :]

@@ -202,9 +202,21 @@ def run_ours(args):
     enc.load_state_dict(syn.make_state_dict(w))
     enc = enc.to(dev, dtype).train()          # training step: dropout active, as the configs set it
     model = enc
-    if world > 1:
+    use_graph = not args.no_graph
+    if world > 1 and not use_graph:
         model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local],
                                                           gradient_as_bucket_view=True)
+    params = [p for p in enc.parameters()]
+
+    def allreduce_grads():
+        """Data-parallel gradient averaging for the graph-replayed step: the encoder's 4.94 M
+        parameter gradients (9.9 MB in bf16) travel as ONE flat bucket through one NCCL all-reduce
+        over NVLink, then are scattered back in place.  (Eager mode uses torch DDP instead.)"""
+        grads = [p.grad for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
     # one synthetic sample per GPU (weak scaling), different per rank
     host = syn.make_encoder_inputs(w, bs=1, seed=rank)
     pin = {k: getattr(host, k).to(dtype).pin_memory()
@@ -234,7 +246,6 @@ def run_ours(args):
     # host then issues one launch per step instead of ~600.  The camera-rig plan (the only part with a
     # host sync) is prepared once, as a deployment with a fixed rig would do.
     graph = None
-    use_graph = (world == 1) and not args.no_graph
     if use_graph:
         plan = enc.prepare(host.img_metas, w.bev_h, w.bev_w, dev)
         static_in = {k: v.clone() for k, v in dev_in.items()}
@@ -287,6 +298,8 @@ def run_ours(args):
 
         def step_resident():                       # noqa: F811 - graph replay replaces the eager step
             graph.replay()
+            if world > 1:
+                allreduce_grads()
             return static_loss
 
     # e2e: every step copies its inputs from pinned host memory and reads the loss back.  The copy of
@@ -316,6 +329,8 @@ def run_ours(args):
                 for k in static_in:
                     static_in[k].copy_(bufs[cur][k])
             graph.replay()
+            if world > 1:
+                allreduce_grads()
             loss = static_loss
         else:
             loss = step({k: v.detach() for k, v in bufs[cur].items()})
@@ -418,7 +433,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "bevformer_base encoder: 6 layers, 200x200 BEV queries, 6 cams, 4 levels "
                                "(116x200..15x25), D=4 pillar points, TSA with prev_bev, fwd+bwd, train mode "
-                               "(dropout 0.1), 1 sample per GPU" + (", DDP gradient all-reduce (NCCL)" if world > 1 else ""),
+                               "(dropout 0.1), 1 sample per GPU" + (", gradient all-reduce over NCCL (one flat 9.9 MB bucket per step)" if world > 1 else ""),
                    "execution": ("whole step (forward + backward) captured in one CUDA graph, replayed per step"
                                  if graph is not None else "eager launches"),
                    "l2": "per-step working set (>1 GB of activations + 95 MB features) exceeds the 126 MB L2; no explicit flush",

@@ -255,12 +255,14 @@ sca_prep_bwd_m8(const float *__restrict__ raw, const float *__restrict__ grad_lo
 }
 
 // column sums of a (rows, C) matrix into fp32 (bias gradients): out[c] += sum_r x[r, c]
+// thread -> (column vector cv, row lane rl); consecutive threads walk along a row (coalesced 16 B
+// loads), four rows in flight per thread; row lanes are combined through shared memory without
+// atomics, then one global atomicAdd per column per CTA.
 template <typename T>
 __global__ void __launch_bounds__(kEThreads)
 colsum_kernel(const T *__restrict__ x, float *__restrict__ out, long long rows, int C, int rows_per_cta) {
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
-    const int per_row = C / VEC;                       // vectors per row
-    // thread -> (column vector cv, row lane rl); consecutive threads walk along a row (coalesced)
+    const int per_row = C / VEC;
     const int cv = threadIdx.x % per_row, rl = threadIdx.x / per_row, rstep = kEThreads / per_row;
     float acc[VEC];
 #pragma unroll
@@ -268,22 +270,74 @@ colsum_kernel(const T *__restrict__ x, float *__restrict__ out, long long rows, 
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min(rows, r0 + rows_per_cta);
     if (rl < rstep) {
-        for (long long r = r0 + rl; r < r1; r += rstep) {
+        long long r = r0 + rl;
+        for (; r + 3ll * rstep < r1; r += 4ll * rstep) {
+            float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+            load_vec<T, VEC>(x + r * C + cv * VEC, v0);
+            load_vec<T, VEC>(x + (r + rstep) * C + cv * VEC, v1);
+            load_vec<T, VEC>(x + (r + 2ll * rstep) * C + cv * VEC, v2);
+            load_vec<T, VEC>(x + (r + 3ll * rstep) * C + cv * VEC, v3);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+        }
+        for (; r < r1; r += rstep) {
             float v[VEC];
             load_vec<T, VEC>(x + r * C + cv * VEC, v);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[k] += v[k];
         }
     }
-    extern __shared__ float s_part[];                  // C floats
-    for (int i = threadIdx.x; i < C; i += kEThreads) s_part[i] = 0.f;
-    __syncthreads();
+    extern __shared__ float s_part[];                  // rstep x C floats
     if (rl < rstep) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) atomicAdd(&s_part[cv * VEC + k], acc[k]);
+        for (int k = 0; k < VEC; ++k) s_part[rl * C + cv * VEC + k] = acc[k];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += kEThreads) atomicAdd(out + i, s_part[i]);
+    for (int c = threadIdx.x; c < C; c += kEThreads) {
+        float t = 0.f;
+        for (int j = 0; j < rstep; ++j) t += s_part[j * C + c];
+        atomicAdd(out + c, t);
+    }
+}
+
+// d_pre = dy * scale wherever the saved activation h is non-zero: the joint backward of
+// dropout(relu(z)) given h = dropout(relu(z)) (h != 0 <=> z > 0 and the element was kept)
+template <typename T>
+__global__ void __launch_bounds__(kEThreads)
+relu_dropout_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ h, T *__restrict__ out,
+                        long long n_vec, float scale) {
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vec) return;
+    float g[VEC], a[VEC];
+    load_vec<T, VEC>(dy + i * VEC, g);
+    load_vec<T, VEC>(h + i * VEC, a);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) g[k] = a[k] != 0.f ? g[k] * scale : 0.f;
+    store_vec<T, VEC>(out + i * VEC, g);
+}
+
+// in-place inverted dropout with Philox bits (no mask tensor): x *= keep / (1 - p)
+template <typename T>
+__global__ void __launch_bounds__(kEThreads)
+dropout_inplace_kernel(T *__restrict__ x, long long n_vec, float p, unsigned long long seed,
+                       const unsigned long long *__restrict__ seed_base) {
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vec) return;
+    if (seed_base) seed += *seed_base;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)i, 0ull, &st);
+    const float scale = 1.f / (1.f - p);
+    float v[VEC];
+    load_vec<T, VEC>(x + i * VEC, v);
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) {
+        const float4 u = curand_uniform4(&st);
+        v[k] = u.x >= p ? v[k] * scale : 0.f; v[k + 1] = u.y >= p ? v[k + 1] * scale : 0.f;
+        v[k + 2] = u.z >= p ? v[k + 2] * scale : 0.f; v[k + 3] = u.w >= p ? v[k + 3] * scale : 0.f;
+    }
+    store_vec<T, VEC>(x + i * VEC, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,9 +439,37 @@ __device__ __forceinline__ void dropout_scale(float (&m)[PER], unsigned long lon
     }
 }
 
+// One lane's share of a row as loaded (16 B vectors), so the NEXT row's loads can be in flight while the
+// current row is reduced.  Chunk ci holds channels [ci*32*VEC + lane*VEC, +VEC).
+template <typename T, int PER> struct RawRow {
+    static constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    static constexpr int NCH = PER / VEC;
+    uint4 q[NCH];
+    __device__ __forceinline__ void load(const T *row_ptr, int lane) {
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci)
+            q[ci] = __ldg(reinterpret_cast<const uint4 *>(row_ptr + ci * 32 * VEC + lane * VEC));
+    }
+    __device__ __forceinline__ void unpack(float (&v)[PER]) const {
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            if constexpr (sizeof(T) == 2) {
+                const uint32_t u[4] = {q[ci].x, q[ci].y, q[ci].z, q[ci].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { v[ci * 8 + 2 * k] = bf16_lo(u[k]); v[ci * 8 + 2 * k + 1] = bf16_hi(u[k]); }
+            } else {
+                v[ci * 4] = __uint_as_float(q[ci].x); v[ci * 4 + 1] = __uint_as_float(q[ci].y);
+                v[ci * 4 + 2] = __uint_as_float(q[ci].z); v[ci * 4 + 3] = __uint_as_float(q[ci].w);
+            }
+        }
+    }
+};
+
 template <typename TP> __device__ __forceinline__ float ldp(const TP *p, int i);
 template <> __device__ __forceinline__ float ldp<float>(const float *p, int i) { return __ldg(p + i); }
 template <> __device__ __forceinline__ float ldp<bf16>(const bf16 *p, int i) { return __bfloat162float(p[i]); }
+
+constexpr int kLnRowsPerWarp = 4;
 
 template <typename T, typename TP, int C>
 __global__ void __launch_bounds__(kEThreads)
@@ -397,64 +479,72 @@ layernorm_fwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
               long long rows, float eps, float drop_p, unsigned long long seed,
               const unsigned long long *__restrict__ seed_base) {
     constexpr int PER = C / 32;                 // channels per lane (8 for C = 256)
-    if (seed_base) seed += *seed_base;          // device-side step counter (CUDA-graph replays)
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
     static_assert(PER % VEC == 0, "C must be a multiple of 32 * VEC");
+    if (seed_base) seed += *seed_base;          // device-side step counter (CUDA-graph replays)
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (kEThreads / 32) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    float v[PER];
+    const long long row0 = ((long long)blockIdx.x * (kEThreads / 32) + (threadIdx.x >> 5)) * kLnRowsPerWarp;
+    if (row0 >= rows) return;
+    float gam[PER], bet[PER];
 #pragma unroll
-    for (int i = 0; i < PER; i += VEC) {
-        const int c = (i / VEC) * 32 * VEC + lane * VEC;
-        float tmp[VEC];
-        load_vec<T, VEC>(x + row * C + c, tmp);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[i + k] = tmp[k];
+    for (int i = 0; i < PER; ++i) {
+        const int c = (i / VEC) * 32 * VEC + lane * VEC + (i % VEC);
+        gam[i] = ldp<TP>(gamma, c); bet[i] = ldp<TP>(beta, c);
     }
-    if (drop_p > 0.f) {
-        float msk[PER];
-        dropout_scale<PER>(msk, seed, row, lane, drop_p);
+    RawRow<T, PER> xr, rr, xn, rn;
+    xr.load(x + row0 * C, lane);
+    if (res) rr.load(res + row0 * C, lane);
+#pragma unroll 1
+    for (int it = 0; it < kLnRowsPerWarp; ++it) {
+        const long long row = row0 + it;
+        if (row >= rows) break;
+        const bool more = (it + 1 < kLnRowsPerWarp) && (row + 1 < rows);
+        if (more) {                              // next row's loads go out before this row's math
+            xn.load(x + (row + 1) * C, lane);
+            if (res) rn.load(res + (row + 1) * C, lane);
+        }
+        float v[PER];
+        xr.unpack(v);
+        if (drop_p > 0.f) {
+            float msk[PER];
+            dropout_scale<PER>(msk, seed, row, lane, drop_p);
 #pragma unroll
-        for (int i = 0; i < PER; ++i) v[i] *= msk[i];
-    }
-    if (res) {
+            for (int i = 0; i < PER; ++i) v[i] *= msk[i];
+        }
+        if (res) {
+            float r2[PER];
+            rr.unpack(r2);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] += r2[i];
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s += v[i];
+        const float mean = warp_sum(s) * (1.f / C);
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; s2 += d * d; }
+        const float rstd = rsqrtf(warp_sum(s2) * (1.f / C) + eps);
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
 #pragma unroll
         for (int i = 0; i < PER; i += VEC) {
             const int c = (i / VEC) * 32 * VEC + lane * VEC;
-            float r2[VEC];
-            load_vec<T, VEC>(res + row * C + c, r2);
+            float o[VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) v[i + k] += r2[k];
+            for (int k = 0; k < VEC; ++k) o[k] = (v[i + k] - mean) * rstd * gam[i + k] + bet[i + k];
+            store_vec<T, VEC>(y + row * C + c, o);
+            if (y2) {
+                float pz[VEC];
+                load_vec<T, VEC>(pos + row * C + c, pz);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) pz[k] += o[k];
+                store_vec<T, VEC>(y2 + row * C + c, pz);
+            }
         }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) s += v[i];
-    const float mean = warp_sum(s) * (1.f / C);
-    float s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; s2 += d * d; }
-    const float rstd = rsqrtf(warp_sum(s2) * (1.f / C) + eps);
-    if (lane == 0) {
-        if (mean_out) mean_out[row] = mean;
-        if (rstd_out) rstd_out[row] = rstd;
-    }
-#pragma unroll
-    for (int i = 0; i < PER; i += VEC) {
-        const int c = (i / VEC) * 32 * VEC + lane * VEC;
-        float o[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-            o[k] = (v[i + k] - mean) * rstd * ldp<TP>(gamma, c + k) + ldp<TP>(beta, c + k);
-        store_vec<T, VEC>(y + row * C + c, o);
-        if (y2) {
-            float pz[VEC];
-            load_vec<T, VEC>(pos + row * C + c, pz);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) pz[k] += o[k];
-            store_vec<T, VEC>(y2 + row * C + c, pz);
-        }
+        xr = xn; rr = rn;
     }
 }
 
@@ -484,7 +574,25 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
         gam[i] = ldp<TP>(gamma, (i / VEC) * 32 * VEC + lane * VEC + (i % VEC));
     }
     const long long row0 = (long long)blockIdx.x * rows_per_cta;
-    for (long long row = row0 + warp; row < row0 + rows_per_cta && row < rows; row += kEThreads / 32) {
+    const long long row_end = min(rows, row0 + (long long)rows_per_cta);
+    constexpr int kStep = kEThreads / 32;
+    RawRow<T, PER> xr, rr, gr, g2r, xn, rn, gn, g2n;
+    long long row = row0 + warp;
+    if (row < row_end) {
+        xr.load(x + row * C, lane);
+        if (res) rr.load(res + row * C, lane);
+        gr.load(dy + row * C, lane);
+        if (dy2) g2r.load(dy2 + row * C, lane);
+    }
+#pragma unroll 1
+    for (; row < row_end; row += kStep) {
+        const long long nxt = row + kStep;
+        if (nxt < row_end) {                     // prefetch the next row of this warp
+            xn.load(x + nxt * C, lane);
+            if (res) rn.load(res + nxt * C, lane);
+            gn.load(dy + nxt * C, lane);
+            if (dy2) g2n.load(dy2 + nxt * C, lane);
+        }
         const float mean = mean_in[row], rstd = rstd_in[row];
         float xh[PER], g[PER], msk[PER];
         if (drop_p > 0.f) {
@@ -493,29 +601,24 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
 #pragma unroll
             for (int i = 0; i < PER; ++i) msk[i] = 1.f;
         }
+        xr.unpack(xh);
+        gr.unpack(g);
 #pragma unroll
-        for (int i = 0; i < PER; i += VEC) {
-            const int c = (i / VEC) * 32 * VEC + lane * VEC;
-            float tx[VEC], tg[VEC];
-            load_vec<T, VEC>(x + row * C + c, tx);
+        for (int i = 0; i < PER; ++i) xh[i] *= msk[i];
+        if (res) {
+            float r2[PER];
+            rr.unpack(r2);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) tx[k] *= msk[i + k];
-            if (res) {
-                float r2[VEC];
-                load_vec<T, VEC>(res + row * C + c, r2);
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) tx[k] += r2[k];
-            }
-            load_vec<T, VEC>(dy + row * C + c, tg);
-            if (dy2) {
-                float t2[VEC];
-                load_vec<T, VEC>(dy2 + row * C + c, t2);
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) tg[k] += t2[k];
-            }
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) { xh[i + k] = (tx[k] - mean) * rstd; g[i + k] = tg[k]; }
+            for (int i = 0; i < PER; ++i) xh[i] += r2[i];
         }
+        if (dy2) {
+            float t2[PER];
+            g2r.unpack(t2);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) g[i] += t2[i];
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) xh[i] = (xh[i] - mean) * rstd;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
@@ -536,6 +639,7 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
             store_vec<T, VEC>(dx + row * C + c, om);
             if (dres) store_vec<T, VEC>(dres + row * C + c, o);
         }
+        xr = xn; rr = rn; gr = gn; g2r = g2n;
     }
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -837,7 +941,7 @@ static int ln_fwd_t(const char *who, const void *x, const void *res, const void 
                     const void *pos, void *y, void *y2, float *mean, float *rstd, long long rows, int C,
                     float eps, float drop_p, unsigned long long seed, const unsigned long long *sb,
                     cudaStream_t st) {
-    const unsigned grid = blocks_for(rows, kEThreads / 32);
+    const unsigned grid = blocks_for(rows, (kEThreads / 32) * kLnRowsPerWarp);
     if (C == 256)
         layernorm_fwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, (const TP *)beta, (const T *)pos, (T *)y, (T *)y2, mean, rstd, rows, eps, drop_p, seed, sb);
     else if (C == 512)
@@ -985,9 +1089,49 @@ extern "C" int bevf_colsum(const void *x, float *out, int64_t rows, int C, int d
     if (rows_per_cta < 64) rows_per_cta = 64;
     const unsigned grid = blocks_for(rows, (int)rows_per_cta);
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t sm = (size_t)(kEThreads / (C / vec)) * C * sizeof(float);
+    BEVF_REQUIRE(sm <= 48 * 1024, who, "C too large for the row-lane staging");
     if (dtype == BEVF_DTYPE_BF16)
-        colsum_kernel<bf16><<<grid, kEThreads, C * sizeof(float), st>>>((const bf16 *)x, out, rows, C, (int)rows_per_cta);
+        colsum_kernel<bf16><<<grid, kEThreads, sm, st>>>((const bf16 *)x, out, rows, C, (int)rows_per_cta);
     else
-        colsum_kernel<float><<<grid, kEThreads, C * sizeof(float), st>>>((const float *)x, out, rows, C, (int)rows_per_cta);
+        colsum_kernel<float><<<grid, kEThreads, sm, st>>>((const float *)x, out, rows, C, (int)rows_per_cta);
+    return check_launch(who);
+}
+
+extern "C" int bevf_relu_dropout_backward(const void *dy, const void *h, void *out, int64_t n, float scale,
+                                          int dtype, void *stream) {
+    const char *who = "bevf_relu_dropout_backward";
+    BEVF_REQUIRE(n >= 0, who, "bad dimension");
+    if (n == 0) return 0;
+    BEVF_REQUIRE(dy && h && out, who, "null pointer argument");
+    const int vec = dtype == BEVF_DTYPE_BF16 ? 8 : 4;
+    BEVF_REQUIRE(dtype == BEVF_DTYPE_BF16 || dtype == BEVF_DTYPE_F32, who, "unsupported dtype code");
+    BEVF_REQUIRE(n % vec == 0, who, "element count must be a multiple of the vector width");
+    const long long nv = n / vec;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BEVF_DTYPE_BF16)
+        relu_dropout_bwd_kernel<bf16><<<blocks_for(nv, kEThreads), kEThreads, 0, st>>>((const bf16 *)dy, (const bf16 *)h, (bf16 *)out, nv, scale);
+    else
+        relu_dropout_bwd_kernel<float><<<blocks_for(nv, kEThreads), kEThreads, 0, st>>>((const float *)dy, (const float *)h, (float *)out, nv, scale);
+    return check_launch(who);
+}
+
+extern "C" int bevf_dropout_inplace(void *x, int64_t n, float p, uint64_t seed, const uint64_t *seed_base,
+                                    int dtype, void *stream) {
+    const char *who = "bevf_dropout_inplace";
+    BEVF_REQUIRE(n >= 0, who, "bad dimension");
+    BEVF_REQUIRE(p >= 0.f && p < 1.f, who, "dropout probability must be in [0, 1)");
+    if (n == 0 || p == 0.f) return 0;
+    BEVF_REQUIRE(x, who, "null pointer argument");
+    const int vec = dtype == BEVF_DTYPE_BF16 ? 8 : 4;
+    BEVF_REQUIRE(dtype == BEVF_DTYPE_BF16 || dtype == BEVF_DTYPE_F32, who, "unsupported dtype code");
+    BEVF_REQUIRE(n % vec == 0, who, "element count must be a multiple of the vector width");
+    const long long nv = n / vec;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long *sb = reinterpret_cast<const unsigned long long *>(seed_base);
+    if (dtype == BEVF_DTYPE_BF16)
+        dropout_inplace_kernel<bf16><<<blocks_for(nv, kEThreads), kEThreads, 0, st>>>((bf16 *)x, nv, p, seed, sb);
+    else
+        dropout_inplace_kernel<float><<<blocks_for(nv, kEThreads), kEThreads, 0, st>>>((float *)x, nv, p, seed, sb);
     return check_launch(who);
 }

@@ -535,3 +535,29 @@ def colsum(x):
         st = lib.bevf_colsum(x.data_ptr(), out.data_ptr(), rows, C, _DT[x.dtype], _stream_ptr(x))
     _lib.check(st, lib)
     return out
+
+
+def dropout_inplace_(x, p):
+    """x *= keep / (1 - p) in place with Philox bits keyed by the device-side step counter."""
+    _need_cuda(x, "x")
+    if p <= 0.0:
+        return x
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = lib.bevf_dropout_inplace(x.data_ptr(), x.numel(), float(p), _next_seed(),
+                                      seed_state(x.device).data_ptr(), _DT[x.dtype], _stream_ptr(x))
+    _lib.check(st, lib)
+    return x
+
+
+def relu_dropout_backward(dy, h, p):
+    """Gradient w.r.t. z of h = dropout_p(relu(z)), from the saved h alone."""
+    _need_cuda(dy, "dy")
+    dy = dy.contiguous()
+    out = torch.empty_like(dy)
+    lib = _lib.load()
+    with torch.cuda.device(dy.device):
+        st = lib.bevf_relu_dropout_backward(dy.data_ptr(), h.data_ptr(), out.data_ptr(), dy.numel(),
+                                            1.0 / (1.0 - p), _DT[dy.dtype], _stream_ptr(dy))
+    _lib.check(st, lib)
+    return out

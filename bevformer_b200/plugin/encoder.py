@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .linear import linear
+from .linear import linear, linear_relu_dropout
 from .registry import (FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, _register,
                        build_attention, build_feedforward_network, build_transformer_layer)
 from .spatial_cross_attention import ScaPlan, SpatialCrossAttention
@@ -64,10 +64,11 @@ class FFN(nn.Module):
         """The stack without the identity add (hidden dropout included, final dropout not)."""
         h = x
         for blk in list(self.layers)[: self.num_fcs - 1]:
-            h = linear(h, blk[0].weight, blk[0].bias, relu=self.act_type == "ReLU")
-            if self.act_type != "ReLU":
-                h = blk[1](h)
-            h = blk[2](h)
+            if self.act_type == "ReLU":
+                p = blk[2].p if blk[2].training else 0.0
+                h = linear_relu_dropout(h, blk[0].weight, blk[0].bias, p)
+            else:
+                h = blk[2](blk[1](linear(h, blk[0].weight, blk[0].bias)))
         last = self.layers[self.num_fcs - 1]
         return linear(h, last.weight, last.bias)
 

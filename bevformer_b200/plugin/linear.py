@@ -48,13 +48,55 @@ class _LinearTC(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_tc(dy2, w.t().contiguous(), None, None, False).view(x.shape)
         if ctx.needs_input_grad[1]:
-            if os.environ.get("BEVF_WGRAD", "tc") != "cublas" and n % 8 == 0:
-                dw = ops.linear_wgrad_tc(dy2, x.reshape(-1, k)).to(ctx.dtypes[0])
-            else:
-                dw = torch.mm(dy2.t(), x.reshape(-1, k)).to(ctx.dtypes[0])
+            dw = _wgrad(dy2, x.reshape(-1, k), n, k, ctx.dtypes[0])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy2).to(ctx.dtypes[1])
         return dx, dw, db, None, None
+
+
+def _wgrad(dy2, x2, n, k, dtype):
+    if os.environ.get("BEVF_WGRAD", "tc") != "cublas" and n % 8 == 0:
+        return ops.linear_wgrad_tc(dy2, x2).to(dtype)
+    return torch.mm(dy2.t(), x2).to(dtype)
+
+
+class _LinearReluDropoutTC(Function):
+    """h = dropout_p(relu(x W^T + b)): ReLU in the GEMM epilogue, dropout in place with Philox bits;
+    the backward needs only h (h != 0 <=> pre-activation > 0 and kept)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p):
+        w = weight.to(torch.bfloat16)
+        xc = x.contiguous()
+        h = ops.linear_tc(xc, w, bias, None, True, torch.bfloat16)
+        ops.dropout_inplace_(h, p)
+        ctx.save_for_backward(xc, w, h)
+        ctx.meta = (bias is not None, weight.dtype, None if bias is None else bias.dtype, float(p))
+        return h
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, h = ctx.saved_tensors
+        has_bias, wdt, bdt, p = ctx.meta
+        k, n = w.shape[1], w.shape[0]
+        dz = ops.relu_dropout_backward(dy.reshape(-1, n), h.reshape(-1, n), p)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_tc(dz, w.t().contiguous(), None, None, False).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dz, x.reshape(-1, k), n, k, wdt)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dz).to(bdt)
+        return dx, dw, db, None
+
+
+def linear_relu_dropout(x, weight, bias, p: float):
+    """FFN hidden layer: Linear -> ReLU -> Dropout(p) (p = 0 outside training)."""
+    if _use_tc(x, weight):
+        return _LinearReluDropoutTC.apply(x, weight, bias, p)
+    y = F.relu(F.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype)), inplace=True)
+    return F.dropout(y, p, training=p > 0.0)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias, relu: bool = False) -> torch.Tensor:

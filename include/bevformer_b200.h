@@ -241,6 +241,20 @@ BEVF_API int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64_t
  * replaces the at::reduce_kernel autograd launches for nn.Linear.bias.grad.  x (rows, C) f32 | bf16. */
 BEVF_API int bevf_colsum(const void *x, float *out, int64_t rows, int C, int dtype, void *stream);
 
+/*
+ * The FFN's hidden dropout (mmcv FFN: Linear -> ReLU -> Dropout; the ReLU itself is fused into
+ * bevf_linear_forward's epilogue) and the joint backward of dropout(relu(z)).
+ *   bevf_dropout_inplace: x *= keep / (1 - p) with Philox4x32-10(seed [+ *seed_base], element / vec) bits,
+ *     no mask tensor.  replaces at::native::fused_dropout.
+ *   bevf_relu_dropout_backward: out = dy * scale where h != 0, else 0, with h the SAVED forward
+ *     activation dropout(relu(z)) (h != 0 <=> z > 0 and kept) and scale = 1 / (1 - p).  replaces
+ *     masked_scale + threshold_backward.  dy, h, out: n elements in `dtype`.
+ */
+BEVF_API int bevf_dropout_inplace(void *x, int64_t n, float p, uint64_t seed, const uint64_t *seed_base,
+                                  int dtype, void *stream);
+BEVF_API int bevf_relu_dropout_backward(const void *dy, const void *h, void *out, int64_t n, float scale,
+                                        int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -661,6 +661,7 @@ struct Wgrad2Params {
     int rows_per_split;    // multiple of 64
     int splits;
     float *dw;
+    float *db;             // (N) f32 bias gradient = column sums of dY, accumulated into; may be null
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -688,7 +689,8 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        // a stage is released by the MMA commit and, when the bias gradient is wanted, by warp 3 too
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.db ? 2 : 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -754,6 +756,61 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
                     umma_commit(&empty[s]);
                     if (kb == kblocks - 1) umma_commit(acc_full);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== bias gradient: column sums of the dY tiles, read from shared memory ====
+        // lane = (16 B unit j = lane % 8 of a 64-column chunk, row group lane / 8); the tile is stored
+        // MN-major with the 128 B swizzle: unit j of K row r sits at position j ^ (r & 7).
+        if (p.db) {
+            int s = 0; uint32_t ph = 0;
+            const int j = lane & 7, rg = lane >> 3;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                int gn, tk, m_begin, kblocks;
+                decode(u, gn, tk, m_begin, kblocks);
+                float acc[4][8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    if (tk == 0) {                                    // count every dY element once
+                        const uint8_t *sa = smem + (size_t)s * stage_bytes;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < p.NB * 2) {
+#pragma unroll 4
+                                for (int r = rg; r < 64; r += 4) {
+                                    const uint4 v = *reinterpret_cast<const uint4 *>(sa + c * kChunk + r * 128 + ((j ^ (r & 7)) << 4));
+                                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) { acc[c][2 * e] += bf16_lo(w4[e]); acc[c][2 * e + 1] += bf16_hi(w4[e]); }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+                if (tk == 0 && kblocks > 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float t = acc[c][e];
+                            t += __shfl_xor_sync(0xffffffffu, t, 8);
+                            t += __shfl_xor_sync(0xffffffffu, t, 16);
+                            acc[c][e] = t;
+                        }
+                        const int col = gn * p.NB * kBM + c * 64 + j * 8;
+                        if (rg == 0 && c < p.NB * 2 && col < p.N) {
+                            red_add_v4(p.db + col, acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                            red_add_v4(p.db + col + 4, acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                        }
+                    }
                 }
             }
         }
@@ -960,13 +1017,14 @@ extern "C" int bevf_linear_forward(const void *x, const void *w, const void *bia
 }
 
 
-extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64_t M, int N, int K,
-                                 void *stream) {
+extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, float *db, int64_t M, int N,
+                                 int K, void *stream) {
     const char *who = "bevf_linear_wgrad";
     if (M < 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
     if (M == 0) return 0;
     if (!dy || !x || !dw) return fail("%s: null pointer argument", who);
     if (K % 64 != 0 || N % 8 != 0) return fail("%s: K must be a multiple of 64 and N of 8", who);
+    if (db && !aligned16(db)) return fail("%s: pointers must be 16-byte aligned", who);
     if (M >= (1ll << 31)) return fail("%s: M too large", who);
     if (!aligned16(dy) || !aligned16(x) || !aligned16(dw)) return fail("%s: pointers must be 16-byte aligned", who);
     int bn = 0;
@@ -991,7 +1049,7 @@ extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64
     }
     if (use_v2) {
         Wgrad2Params q;
-        q.M = (int)M; q.N = N; q.K = K; q.BN = bn; q.dw = dw;
+        q.M = (int)M; q.N = N; q.K = K; q.BN = bn; q.dw = dw; q.db = db;
         const int blocks_n = (N + kBM - 1) / kBM;
         q.NB = (blocks_n >= 2 && 2 * bn <= 512) ? 2 : 1;
         const int groups = (blocks_n + q.NB - 1) / q.NB;
@@ -1012,6 +1070,7 @@ extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64
         gemm_wgrad2_bf16<<<grid2, kGemmThreads, smem2, (cudaStream_t)stream>>>(map_dy, map_x, q);
         return check_launch(who);
     }
+    if (db) return fail("%s: the bias gradient needs the v2 kernel (unset BEVF_WGRAD_V2=0)", who);
     WgradParams p;
     p.M = (int)M; p.N = N; p.K = K; p.BN = bn; p.dw = dw;
     const int tiles = ((N + kBM - 1) / kBM) * (K / bn);

@@ -508,20 +508,25 @@ def linear_tc(x, weight, bias=None, residual=None, relu=False, out_dtype=None):
     return y
 
 
-def linear_wgrad_tc(dy, x):
-    """dW = dy^T @ x on the tcgen05 split-M kernel. dy (M, N) bf16, x (M, K) bf16 -> (N, K) fp32."""
+def linear_wgrad_tc(dy, x, with_bias=False):
+    """dW = dy^T @ x on the tcgen05 split-M kernel (and db = column sums of dy from the same pass).
+    dy (M, N) bf16, x (M, K) bf16 -> (N, K) fp32 [, (N,) fp32]."""
     _need_cuda(dy, "dy")
     _need_cuda(x, "x")
     if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.shape[0] != x.shape[0]:
         raise RuntimeError("linear_wgrad_tc: dy (M,N) and x (M,K) must be bfloat16 with equal M")
     M, N = dy.shape
     K = x.shape[1]
-    dw = torch.zeros((N, K), device=x.device, dtype=torch.float32)
+    npad = (N + 3) // 4 * 4
+    buf = torch.zeros(N * K + (npad if with_bias else 0), device=x.device, dtype=torch.float32)
+    dw = buf[: N * K].view(N, K)
+    db = buf[N * K: N * K + N] if with_bias else None
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        st = lib.bevf_linear_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, N, K, _stream_ptr(x))
+        st = lib.bevf_linear_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _ptr(db), M, N, K,
+                                   _stream_ptr(x))
     _lib.check(st, lib)
-    return dw
+    return (dw, db) if with_bias else dw
 
 
 def colsum(x):

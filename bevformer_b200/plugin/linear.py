@@ -48,16 +48,22 @@ class _LinearTC(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_tc(dy2, w.t().contiguous(), None, None, False).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy2, x.reshape(-1, k), n, k, ctx.dtypes[0])
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dw, db = _wgrad(dy2, x.reshape(-1, k), n, k, ctx.dtypes[0],
+                            ctx.dtypes[1] if ctx.has_bias else None)
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy2).to(ctx.dtypes[1])
         return dx, dw, db, None, None
 
 
-def _wgrad(dy2, x2, n, k, dtype):
+def _wgrad(dy2, x2, n, k, wdtype, bdtype=None):
+    """(dW, db) of a projection; db comes out of the same kernel pass as dW when requested."""
     if os.environ.get("BEVF_WGRAD", "tc") != "cublas" and n % 8 == 0:
-        return ops.linear_wgrad_tc(dy2, x2).to(dtype)
-    return torch.mm(dy2.t(), x2).to(dtype)
+        if bdtype is None:
+            return ops.linear_wgrad_tc(dy2, x2).to(wdtype), None
+        dw, db = ops.linear_wgrad_tc(dy2, x2, with_bias=True)
+        return dw.to(wdtype), db.to(bdtype)
+    dw = torch.mm(dy2.t(), x2).to(wdtype)
+    return dw, (None if bdtype is None else ops.colsum(dy2).to(bdtype))
 
 
 class _LinearReluDropoutTC(Function):
@@ -85,8 +91,8 @@ class _LinearReluDropoutTC(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_tc(dz, w.t().contiguous(), None, None, False).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dz, x.reshape(-1, k), n, k, wdt)
-        if has_bias and ctx.needs_input_grad[2]:
+            dw, db = _wgrad(dz, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None)
+        elif has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dz).to(bdt)
         return dx, dw, db, None
 

@@ -232,10 +232,12 @@ BEVF_API int bevf_linear_forward(const void *x, const void *w, const void *bias,
  * Weight gradient of the projection above:  dw[N,K] += dy[M,N]^T . x[M,K]   (fp32, ACCUMULATED
  * INTO: the caller zero-fills).  dy, x bf16 row-major; split over the M rows across the SMs, partial
  * tiles combined with 16 B fp32 reductions.  replaces the cuBLAS call autograd makes for
- * nn.Linear.weight.grad.  K % 64 == 0, N % 8 == 0.
+ * nn.Linear.weight.grad.  K % 64 == 0, N % 8 == 0.  db (N) f32, optional: the bias gradient
+ * db[n] += sum_m dy[m, n], summed from the dY tiles while they sit in shared memory (no second pass
+ * over dy; replaces the at::reduce_kernel behind nn.Linear.bias.grad).
  */
-BEVF_API int bevf_linear_wgrad(const void *dy, const void *x, float *dw, int64_t M, int N, int K,
-                               void *stream);
+BEVF_API int bevf_linear_wgrad(const void *dy, const void *x, float *dw, float *db, int64_t M, int N,
+                               int K, void *stream);
 
 /* out[c] += sum over rows of x[r, c]  (fp32, ACCUMULATED INTO).  The bias gradient of the projections:
  * replaces the at::reduce_kernel autograd launches for nn.Linear.bias.grad.  x (rows, C) f32 | bf16. */

@@ -67,12 +67,16 @@ WGRAD_SCRIPT = textwrap.dedent("""
     g = torch.Generator().manual_seed(M + N + K)
     dy = torch.randn(M, N, generator=g).bfloat16().cuda()
     x = torch.randn(M, K, generator=g).bfloat16().cuda()
-    dw = ops.linear_wgrad_tc(dy, x)
+    dw, db = ops.linear_wgrad_tc(dy, x, with_bias=True)
     torch.cuda.synchronize()
     ref = dy.float().t() @ x.float()
     err = (dw - ref).abs().max().item() / max(1.0, ref.abs().max().item())
-    print("ERR", err, flush=True)
-    assert err < 2e-3, err
+    refb = dy.double().sum(0)
+    errb = (db.double() - refb).abs().max().item() / max(1.0, refb.abs().max().item())
+    print("ERR", err, errb, flush=True)
+    assert err < 2e-3 and errb < 1e-4, (err, errb)
+    dw2 = ops.linear_wgrad_tc(dy, x)
+    assert (dw2 - ref).abs().max().item() / max(1.0, ref.abs().max().item()) < 2e-3
 """)
 
 

@@ -662,6 +662,9 @@ struct Wgrad2Params {
     int splits;
     float *dw;
     float *db;             // (N) f32 bias gradient = column sums of dY, accumulated into; may be null
+    float *ws;             // two-pass mode: (splits, n_pad, K) partial tiles, plain stores; else null
+    float *ws_b;           // two-pass mode: (splits, n_pad) partial column sums
+    int n_pad;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -806,9 +809,15 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
                             acc[c][e] = t;
                         }
                         const int col = gn * p.NB * kBM + c * 64 + j * 8;
-                        if (rg == 0 && c < p.NB * 2 && col < p.N) {
-                            red_add_v4(p.db + col, acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
-                            red_add_v4(p.db + col + 4, acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                        if (rg == 0 && c < p.NB * 2) {
+                            if (p.ws_b) {
+                                float *dst = p.ws_b + (size_t)(u % p.splits) * p.n_pad + col;
+                                *reinterpret_cast<float4 *>(dst) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                                *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                            } else if (col < p.N) {
+                                red_add_v4(p.db + col, acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                                red_add_v4(p.db + col + 4, acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+                            }
                         }
                     }
                 }
@@ -832,7 +841,18 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
                     tmem_ld16(taddr + (uint32_t)c0, r[0]);
                     tmem_ld16(taddr + (uint32_t)(c0 + 16), r[1]);
                     tmem_ld_wait();
-                    if (row < p.N) {
+                    if (p.ws) {
+                        // two-pass: this split's partial tile goes to its own slab with plain stores
+                        const int split = u % p.splits;
+                        float *dst = p.ws + ((size_t)split * p.n_pad + row) * p.K + tk * p.BN + c0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4 *>(dst + 16 * h + i) =
+                                    make_float4(__uint_as_float(r[h][i]), __uint_as_float(r[h][i + 1]),
+                                                __uint_as_float(r[h][i + 2]), __uint_as_float(r[h][i + 3]));
+                    } else if (row < p.N) {
                         float *dst = p.dw + (size_t)row * p.K + tk * p.BN + c0;
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
@@ -853,6 +873,38 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// second pass of the two-pass weight gradient: dW[n, k] = sum over splits of the partial slabs, written
+// in the parameter's own dtype (no zero-fill, no cast kernel); db likewise.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ ws_b, TO *__restrict__ dw,
+                    TO *__restrict__ db, int N, int K, int n_pad, int splits) {
+    const int kv = K / 4;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * kv;
+    if (t < total) {
+        const int n = (int)(t / kv), c = (int)(t % kv) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *src = ws + (size_t)n * K + c;
+        const size_t slab = (size_t)n_pad * K;
+#pragma unroll 4
+        for (int s2 = 0; s2 < splits; ++s2) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(src + s2 * slab));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if constexpr (sizeof(TO) == 2) {
+            *reinterpret_cast<uint2 *>(dw + (size_t)n * K + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        } else {
+            *reinterpret_cast<float4 *>(dw + (size_t)n * K + c) = a;
+        }
+    } else if (db && t < total + N) {
+        const int n = (int)(t - total);
+        float a = 0.f;
+        for (int s2 = 0; s2 < splits; ++s2) a += ws_b[(size_t)s2 * n_pad + n];
+        if constexpr (sizeof(TO) == 2) db[n] = __float2bfloat16_rn(a); else db[n] = a;
     }
 }
 
@@ -1050,6 +1102,7 @@ extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, float
     if (use_v2) {
         Wgrad2Params q;
         q.M = (int)M; q.N = N; q.K = K; q.BN = bn; q.dw = dw; q.db = db;
+        q.ws = nullptr; q.ws_b = nullptr; q.n_pad = 0;
         const int blocks_n = (N + kBM - 1) / kBM;
         q.NB = (blocks_n >= 2 && 2 * bn <= 512) ? 2 : 1;
         const int groups = (blocks_n + q.NB - 1) / q.NB;
@@ -1087,5 +1140,83 @@ extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, float
     const int units = tiles * splits;
     const int grid = units < num_sms ? units : num_sms;
     gemm_wgrad_bf16<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_dy, map_x, p);
+    return check_launch(who);
+}
+
+
+// plan shared by the workspace query and the launch
+static void wgrad_plan(int64_t M, int N, int K, int num_sms, int &bn, int &NB, int &splits, int &rows, int &n_pad) {
+    bn = 0;
+    for (int c : {256, 192, 128, 64}) if (K % c == 0) { bn = c; break; }
+    const int blocks_n = (N + kBM - 1) / kBM;
+    NB = (blocks_n >= 2 && 2 * bn <= 512) ? 2 : 1;
+    const int groups = (blocks_n + NB - 1) / NB;
+    const int tiles = groups * (K / bn);
+    splits = (num_sms + tiles - 1) / tiles;
+    rows = (int)((M + splits - 1) / splits);
+    rows = ((rows + 63) / 64) * 64;
+    splits = (int)((M + rows - 1) / rows);
+    n_pad = groups * NB * kBM;
+}
+
+extern "C" int64_t bevf_linear_wgrad_workspace_bytes(int64_t M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int bn, NB, splits, rows, n_pad;
+    wgrad_plan(M, N, K, sms, bn, NB, splits, rows, n_pad);
+    return (int64_t)splits * n_pad * ((int64_t)K + 1) * 4 + 256;
+}
+
+extern "C" int bevf_linear_wgrad_out(const void *dy, const void *x, void *dw, void *db, int grad_dtype,
+                                     void *workspace, int64_t workspace_bytes, int64_t M, int N, int K,
+                                     void *stream) {
+    const char *who = "bevf_linear_wgrad_out";
+    if (M <= 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
+    if (!dy || !x || !dw || !workspace) return fail("%s: null pointer argument", who);
+    if (K % 64 != 0 || N % 8 != 0) return fail("%s: K must be a multiple of 64 and N of 8", who);
+    if (M >= (1ll << 31)) return fail("%s: M too large", who);
+    if (!aligned16(dy) || !aligned16(x) || !aligned16(dw) || !aligned16(workspace))
+        return fail("%s: pointers must be 16-byte aligned", who);
+    if (grad_dtype != BEVF_DTYPE_BF16 && grad_dtype != BEVF_DTYPE_F32) return fail("%s: unsupported dtype code", who);
+    if (workspace_bytes < bevf_linear_wgrad_workspace_bytes(M, N, K))
+        return fail("%s: workspace too small (need %lld bytes)", who, bevf_linear_wgrad_workspace_bytes(M, N, K));
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_wgrad2_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    Wgrad2Params q;
+    int rows;
+    wgrad_plan(M, N, K, sms, q.BN, q.NB, q.splits, rows, q.n_pad);
+    q.M = (int)M; q.N = N; q.K = K; q.rows_per_split = rows;
+    q.dw = nullptr; q.db = db ? reinterpret_cast<float *>(1) : nullptr;   // non-null => warp 3 sums columns
+    q.ws = reinterpret_cast<float *>(workspace);
+    q.ws_b = q.ws + (size_t)q.splits * q.n_pad * K;
+    CUtensorMap map_dy, map_x;
+    if (int e = make_map_2d(&map_dy, dy, (uint64_t)M, (uint64_t)N, 64))
+        return fail("%s: cuTensorMapEncodeTiled(dY) failed (%lld)", who, e);
+    if (int e = make_map_2d(&map_x, x, (uint64_t)M, (uint64_t)K, 64))
+        return fail("%s: cuTensorMapEncodeTiled(X) failed (%lld)", who, e);
+    const int stage = q.NB * 2 * 8192 + (q.BN / 64) * 8192;
+    int st = (216 * 1024) / stage;
+    if (st > 6) st = 6;
+    if (st < 2) st = 2;
+    q.stages = st;
+    const size_t smem = (size_t)st * stage + 1024 + (2 * st + 2) * 8 + 16;
+    const int groups = q.n_pad / (q.NB * kBM);
+    const int units = groups * (K / q.BN) * q.splits;
+    const int grid = units < sms ? units : sms;
+    cudaStream_t cs = (cudaStream_t)stream;
+    gemm_wgrad2_bf16<<<grid, kGemmThreads, smem, cs>>>(map_dy, map_x, q);
+    if (int e = check_launch(who)) return e;
+    const long long total = (long long)N * (K / 4) + (db ? N : 0);
+    const unsigned rgrid = (unsigned)((total + 255) / 256);
+    if (grad_dtype == BEVF_DTYPE_BF16)
+        wgrad_reduce_kernel<bf16><<<rgrid, 256, 0, cs>>>(q.ws, q.ws_b, (bf16 *)dw, (bf16 *)db, N, K, q.n_pad, q.splits);
+    else
+        wgrad_reduce_kernel<float><<<rgrid, 256, 0, cs>>>(q.ws, q.ws_b, (float *)dw, (float *)db, N, K, q.n_pad, q.splits);
     return check_launch(who);
 }

@@ -529,6 +529,26 @@ def linear_wgrad_tc(dy, x, with_bias=False):
     return (dw, db) if with_bias else dw
 
 
+def linear_wgrad_out(dy, x, grad_dtype, with_bias):
+    """Two-pass weight (+ bias) gradient written directly in ``grad_dtype``: returns (dW, db|None)."""
+    _need_cuda(dy, "dy")
+    _need_cuda(x, "x")
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.shape[0] != x.shape[0]:
+        raise RuntimeError("linear_wgrad_out: dy (M,N) and x (M,K) must be bfloat16 with equal M")
+    M, N = dy.shape
+    K = x.shape[1]
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        need = int(lib.bevf_linear_wgrad_workspace_bytes(M, N, K))
+        ws = torch.empty(need, device=x.device, dtype=torch.uint8)
+        dw = torch.empty((N, K), device=x.device, dtype=grad_dtype)
+        db = torch.empty((N,), device=x.device, dtype=grad_dtype) if with_bias else None
+        st = lib.bevf_linear_wgrad_out(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _ptr(db),
+                                       _DT[grad_dtype], ws.data_ptr(), need, M, N, K, _stream_ptr(x))
+    _lib.check(st, lib)
+    return dw, db
+
+
 def colsum(x):
     """fp32 column sums of a (rows, C) tensor (bias gradients)."""
     _need_cuda(x, "x")

@@ -257,6 +257,18 @@ BEVF_API int bevf_dropout_inplace(void *x, int64_t n, float p, uint64_t seed, co
 BEVF_API int bevf_relu_dropout_backward(const void *dy, const void *h, void *out, int64_t n, float scale,
                                         int dtype, void *stream);
 
+/*
+ * Two-pass form of the weight (+ bias) gradient: every split of the M rows stores its partial 128-row
+ * tiles into its own slab of `workspace` with plain stores (no 148-way contended reductions), then a
+ * small kernel sums the slabs and writes dw (N, K) and db (N) -- fully OVERWRITTEN, in grad_dtype
+ * (f32 | bf16, i.e. the parameter's dtype: no zero-fill and no cast launch around the call).
+ * bevf_linear_wgrad_workspace_bytes gives the scratch size for a problem; db may be NULL.
+ */
+BEVF_API int64_t bevf_linear_wgrad_workspace_bytes(int64_t M, int N, int K);
+BEVF_API int bevf_linear_wgrad_out(const void *dy, const void *x, void *dw, void *db, int grad_dtype,
+                                   void *workspace, int64_t workspace_bytes, int64_t M, int N, int K,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

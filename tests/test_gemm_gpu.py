@@ -77,6 +77,15 @@ WGRAD_SCRIPT = textwrap.dedent("""
     assert err < 2e-3 and errb < 1e-4, (err, errb)
     dw2 = ops.linear_wgrad_tc(dy, x)
     assert (dw2 - ref).abs().max().item() / max(1.0, ref.abs().max().item()) < 2e-3
+    # two-pass form, outputs written directly in the parameter dtype
+    for gdt, tol in ((torch.float32, 2e-3), (torch.bfloat16, 1e-2)):
+        dw3, db3 = ops.linear_wgrad_out(dy, x, gdt, True)
+        assert dw3.dtype == gdt and db3.dtype == gdt
+        e3 = (dw3.float() - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        e3b = (db3.double() - refb).abs().max().item() / max(1.0, refb.abs().max().item())
+        assert e3 < tol and e3b < tol, (gdt, e3, e3b)
+    dw4, none = ops.linear_wgrad_out(dy, x, torch.float32, False)
+    assert none is None and (dw4 - ref).abs().max().item() / max(1.0, ref.abs().max().item()) < 2e-3
 """)
 
 

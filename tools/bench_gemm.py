@@ -57,11 +57,12 @@ def main():
             continue
         t = timed(lambda: ops.linear_tc(x, w, b, None, relu, od), args.iters, flush)
         tw = timed(lambda: ops.linear_wgrad_tc(dy, x), args.iters, flush)
+        tw2 = timed(lambda: ops.linear_wgrad_out(dy, x, torch.bfloat16, True), args.iters, flush)
         tl = timed(lambda: torch.nn.functional.linear(x, w, b), args.iters, flush)
         byts = M * K * 2 + M * N * (4 if f32 else 2) + N * K * 2
         bw = M * (K + N) * 2 + N * K * 4
         print(json.dumps(dict(shape=name, M=M, N=N, K=K, tc_us=round(t * 1e3, 1), cublas_us=round(tl * 1e3, 1),
-                              wgrad_us=round(tw * 1e3, 1), tc_GBs=round(byts / t / 1e6, 1),
+                              wgrad_us=round(tw * 1e3, 1), wgrad_2pass_us=round(tw2 * 1e3, 1), tc_GBs=round(byts / t / 1e6, 1),
                               tc_frac=round(byts / t / 1e6 / hbm, 3), wgrad_frac=round(bw / tw / 1e6 / hbm, 3),
                               tflops=round(2 * M * N * K / t / 1e9, 1))), flush=True)
 

@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(kEThreads)
 tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
             const float *__restrict__ grad_loc, const float *__restrict__ grad_attn,
             const int64_t *__restrict__ level_hw, float *__restrict__ loc, float *__restrict__ attn,
-            float *__restrict__ d_raw, int B, int Nq, int L, int P, int pmagic) {
+            float *__restrict__ d_raw, int B, int Nq, int L, int P, int pmagic, int interleave) {
     constexpr int M = 8;
     __shared__ float s_w[16], s_h[16];
     if ((int)threadIdx.x < L) { s_h[threadIdx.x] = (float)level_hw[2 * threadIdx.x]; s_w[threadIdx.x] = (float)level_hw[2 * threadIdx.x + 1]; }
@@ -775,8 +775,11 @@ tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
     const long long rbase = bq * (M * 2 * LP * 3);
     const long long o_off = rbase + ((m * 2 + j) * LP + k0) * 2;
     const long long o_lg = rbase + M * 2 * LP * 2 + (m * 2 + j) * LP + k0;
-    const long long orow = ((long long)b * 2 + j) * Nq + q;
-    const long long o_out = (orow * M + m) * LP + k0;
+    const long long orow = ((long long)b * 2 + j) * Nq + q;            // row of ref2d (frame-major)
+    // output rows: frame-major (b, j, q) like the reference, or interleaved (b, q, j) so that the two
+    // frames of a query are adjacent and their mean folds into the output projection
+    const long long out_row = interleave ? (((long long)b * Nq + q) * 2 + j) : orow;
+    const long long o_out = (out_row * M + m) * LP + k0;
     float a[PPL];
     ldv<PPL>(raw + o_lg, a);
     float mx = a[0];
@@ -825,13 +828,14 @@ tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
 template <bool kBackward>
 static bool launch_tsa_prep_m8(const float *raw, const float *ref2d, const float *grad_loc,
                                const float *grad_attn, const int64_t *level_hw, float *loc, float *attn,
-                               float *d_raw, int B, int Nq, int M, int L, int P, cudaStream_t st) {
+                               float *d_raw, int B, int Nq, int M, int L, int P, int interleave,
+                               cudaStream_t st) {
     const int LP = L * P;
     if (!(M == 8 && L <= 16 && LP * P < 65536 && (LP == 2 || LP == 4 || LP == 8 || LP == 16 || LP == 32)))
         return false;
     const int pmagic = (65536 + P - 1) / P;
     const unsigned grid = (unsigned)(((long long)B * Nq + kEThreads / 32 - 1) / (kEThreads / 32));
-#define BEVF_TSA_CASE(N) tsa_prep_m8<N, kBackward><<<grid, kEThreads, 0, st>>>(raw, ref2d, grad_loc, grad_attn, level_hw, loc, attn, d_raw, B, Nq, L, P, pmagic)
+#define BEVF_TSA_CASE(N) tsa_prep_m8<N, kBackward><<<grid, kEThreads, 0, st>>>(raw, ref2d, grad_loc, grad_attn, level_hw, loc, attn, d_raw, B, Nq, L, P, pmagic, interleave)
     switch (LP / 2) {
         case 1: BEVF_TSA_CASE(1); break;
         case 2: BEVF_TSA_CASE(2); break;
@@ -908,31 +912,35 @@ extern "C" int bevf_sca_prep_backward(const float *raw, const float *grad_loc,
 
 extern "C" int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const int64_t *level_hw,
                                      float *loc, float *attn, int B, int Nq, int M, int L, int P,
-                                     void *stream) {
+                                     int interleave, void *stream) {
     const char *who = "bevf_tsa_prep_forward";
     BEVF_REQUIRE(B >= 0 && Nq >= 0 && M > 0 && L > 0 && P > 0, who, "bad dimension");
     const long long total = (long long)B * Nq * M * 2;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && ref2d && level_hw && loc && attn, who, "null pointer argument");
     if (!launch_tsa_prep_m8<false>(raw, ref2d, nullptr, nullptr, level_hw, loc, attn, nullptr, B, Nq, M, L, P,
-                                   (cudaStream_t)stream))
+                                   interleave, (cudaStream_t)stream)) {
+        if (interleave) return fail("%s: interleaved rows need num_heads == 8 and L*P in {2,4,8,16,32}", who);
         tsa_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
             raw, ref2d, level_hw, loc, attn, B, Nq, M, L, P);
+    }
     return check_launch(who);
 }
 
 extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
                                       const float *grad_attn, const int64_t *level_hw, float *d_raw,
-                                      int B, int Nq, int M, int L, int P, void *stream) {
+                                      int B, int Nq, int M, int L, int P, int interleave, void *stream) {
     const char *who = "bevf_tsa_prep_backward";
     BEVF_REQUIRE(B >= 0 && Nq >= 0 && M > 0 && L > 0 && P > 0, who, "bad dimension");
     const long long total = (long long)B * Nq * M * 2;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && grad_loc && grad_attn && level_hw && d_raw, who, "null pointer argument");
     if (!launch_tsa_prep_m8<true>(raw, nullptr, grad_loc, grad_attn, level_hw, nullptr, nullptr, d_raw, B, Nq, M,
-                                  L, P, (cudaStream_t)stream))
+                                  L, P, interleave, (cudaStream_t)stream)) {
+        if (interleave) return fail("%s: interleaved rows need num_heads == 8 and L*P in {2,4,8,16,32}", who);
         tsa_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
             raw, grad_loc, grad_attn, level_hw, d_raw, B, Nq, M, L, P);
+    }
     return check_launch(who);
 }
 

@@ -302,25 +302,26 @@ class ScaPrep(Function):
         return (d_raw,) + (None,) * 10
 
 
-def tsa_prep_forward(raw, ref2d, level_hw, B, Nq, M, L, P):
+def tsa_prep_forward(raw, ref2d, level_hw, B, Nq, M, L, P, interleave=False):
     _need_cuda(raw, "raw")
-    loc = torch.empty((B * 2, Nq, M, L, P, 2), device=raw.device, dtype=torch.float32)
-    attn = torch.empty((B * 2, Nq, M, L, P), device=raw.device, dtype=torch.float32)
+    shape = (B * Nq * 2, M, L, P) if interleave else (B * 2, Nq, M, L, P)
+    loc = torch.empty(shape + (2,), device=raw.device, dtype=torch.float32)
+    attn = torch.empty(shape, device=raw.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(raw.device):
         st = lib.bevf_tsa_prep_forward(raw.data_ptr(), ref2d.data_ptr(), level_hw.data_ptr(),
                                        loc.data_ptr(), attn.data_ptr(), B, Nq, M, L, P,
-                                       _stream_ptr(raw))
+                                       int(interleave), _stream_ptr(raw))
     _lib.check(st, lib)
     return loc, attn
 
 
 class TsaPrep(Function):
     @staticmethod
-    def forward(ctx, raw, ref2d, level_hw, B, Nq, M, L, P):
-        loc, attn = tsa_prep_forward(raw, ref2d, level_hw, B, Nq, M, L, P)
+    def forward(ctx, raw, ref2d, level_hw, B, Nq, M, L, P, interleave=False):
+        loc, attn = tsa_prep_forward(raw, ref2d, level_hw, B, Nq, M, L, P, interleave)
         ctx.save_for_backward(raw, level_hw)
-        ctx.dims = (B, Nq, M, L, P)
+        ctx.dims = (B, Nq, M, L, P, int(interleave))
         return loc, attn
 
     @staticmethod
@@ -334,7 +335,7 @@ class TsaPrep(Function):
                                             grad_attn.contiguous().data_ptr(), level_hw.data_ptr(),
                                             d_raw.data_ptr(), *ctx.dims, _stream_ptr(raw))
         _lib.check(st, lib)
-        return (d_raw,) + (None,) * 7
+        return (d_raw,) + (None,) * 8
 
 
 def _ptr(t):

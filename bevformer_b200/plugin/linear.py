@@ -57,7 +57,7 @@ class _LinearTC(Function):
 
 def _wgrad(dy2, x2, n, k, wdtype, bdtype=None):
     """(dW, db) of a projection; db comes out of the same kernel pass as dW when requested."""
-    mode = os.environ.get("BEVF_WGRAD", "tc2")
+    mode = os.environ.get("BEVF_WGRAD", "tc")     # "tc2": two-pass variant (measured slower, profiles/README.md)
     if mode == "tc2" and n % 8 == 0 and wdtype in (torch.bfloat16, torch.float32) and bdtype in (None, wdtype):
         return ops.linear_wgrad_out(dy2, x2, wdtype, bdtype is not None)
     if mode != "cublas" and n % 8 == 0:

@@ -105,6 +105,16 @@ class TemporalSelfAttention(nn.Module):
         lsi = torch.as_tensor(level_start_index).to(device=query.device, dtype=torch.int64)
         if reference_points.shape[-1] == 2:
             ref = reference_points.reshape(bs * 2, nq, self.num_levels, 2).float().contiguous()
+            lp = self.num_levels * self.num_points
+            if self.num_heads == 8 and lp in (2, 4, 8, 16, 32) and nv == nq:
+                # interleaved rows (b, q, frame): the sampler writes (bs*Nq, 2C) and the mean over the
+                # two frames (:257-265) is folded into the output projection as [W | W] / 2 -- no
+                # reduction kernel forward, no scatter of the gradient to the two frames backward
+                loc, attn = ops.TsaPrep.apply(raw, ref, ss.contiguous(), bs, nq, self.num_heads,
+                                              self.num_levels, self.num_points, True)
+                out = ops.SamplerRows.apply(v, loc, attn, self._frame_map(bs, nq, query.device), ss, lsi)
+                w2 = torch.cat([self.output_proj.weight, self.output_proj.weight], 1) * 0.5
+                return linear(out.view(bs, nq, 2 * c), w2, self.output_proj.bias)
             loc, attn = ops.TsaPrep.apply(raw, ref, ss.contiguous(), bs, nq, self.num_heads,
                                           self.num_levels, self.num_points)
         elif reference_points.shape[-1] == 4:
@@ -118,6 +128,15 @@ class TemporalSelfAttention(nn.Module):
         out = out.view(bs, 2, nq, c)
         pair_sum = out[:, 0] + out[:, 1]
         return linear(pair_sum, self.output_proj.weight * 0.5, self.output_proj.bias)
+
+    def _frame_map(self, bs, nq, device):
+        """value-map index (b*2 + frame) of every interleaved sampler row; cached per shape."""
+        key = (bs, nq, str(device))
+        cache = self.__dict__.setdefault("_frame_map_cache", {})
+        if key not in cache:
+            r = torch.arange(bs * nq * 2, device=device, dtype=torch.int32)
+            cache[key] = ((r // (2 * nq)) * 2 + (r % 2)).contiguous()
+        return cache[key]
 
     def _box_points(self, raw, reference_points, bs, nq):
         """(cx, cy, w, h) reference boxes (:231-235); rare path, spelled with tensor ops."""

@@ -153,14 +153,17 @@ BEVF_API int bevf_sca_prep_backward(const float *raw, const float *grad_loc, con
  *   raw    (B*Nq, M*2*L*P*3) f32: [offsets (M,2,L,P,2) | logits (M,2,L*P)]
  *   ref2d  (B*2, Nq, L, 2) f32 (the encoder's hybird_ref_2d)
  *   loc    (B*2, Nq, M, L, P, 2) f32 out     attn (B*2, Nq, M, L, P) f32 out
+ *   interleave != 0 orders the output rows (b, q, frame) instead of (b, frame, q): the two frames of a
+ *   query become adjacent rows, so the row-list sampler's output is (B*Nq, 2*C) and the average over
+ *   the frames (temporal_self_attention.py:257-265) folds into the output projection.
  */
 BEVF_API int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const int64_t *level_hw,
                                    float *loc, float *attn, int B, int Nq, int M, int L, int P,
-                                   void *stream);
+                                   int interleave, void *stream);
 
 BEVF_API int bevf_tsa_prep_backward(const float *raw, const float *grad_loc, const float *grad_attn,
                                     const int64_t *level_hw, float *d_raw, int B, int Nq, int M,
-                                    int L, int P, void *stream);
+                                    int L, int P, int interleave, void *stream);
 
 /*
  * y = LayerNorm(dropout(x) + residual) * gamma + beta, optionally also y_plus_pos = y + pos.

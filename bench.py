@@ -45,6 +45,14 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle restatement on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
+def cpu_threads() -> int:
+    """Threads for the CPU arm.  PyTorch's CPU kernels on this path stop scaling (and then regress)
+    well before 128 threads, so the arm uses min(host cores, BEVF_CPU_THREADS or 32) and reports that
+    number as `cores`."""
+    cap = int(os.environ.get("BEVF_CPU_THREADS", "32"))
+    return max(1, min(os.cpu_count() or 1, cap))
+
+
 def cpu_reference_step_factory(layers_in_sample=1, bev_div=1):
     """Returns (step_fn, queries_equivalent_per_step).  Sample = `layers_in_sample` of the 6 encoder
     layers, forward + backward, on the full base inputs (optionally a bev_div-times coarser BEV
@@ -54,7 +62,7 @@ def cpu_reference_step_factory(layers_in_sample=1, bev_div=1):
     if bev_div > 1:
         import dataclasses
         w = dataclasses.replace(w, bev_h=w.bev_h // bev_div, bev_w=w.bev_w // bev_div)
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     sd = {k: v.requires_grad_(True) for k, v in syn.make_state_dict(w).items()}
     inp = syn.make_encoder_inputs(w, bs=1, seed=0)
     inp.bev_query.requires_grad_(True)
@@ -76,7 +84,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     step, q_per_step, w = cpu_reference_step_factory(1, 1)
     t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
     bev_div = 1
@@ -413,7 +421,10 @@ def run_ours(args):
         ab = sca_alg_bytes(w, pairs, True)
         roof = {"bound": "hbm", "kernel": "msda_bwd_d32<bf16,bf16> (SCA sampler backward)",
                 "achieved": ab / t_bwd / 1e6, "peak": peak, "unit": "GB/s",
-                "frac": ab / t_bwd / 1e6 / peak, "peak_source": peak_src, "traffic": None,
+                "frac": ab / t_bwd / 1e6 / peak, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
+                # `ncu --set full` capture profiles/r1e_ncu_full_msda_bwd_raw.csv (same kernel build)
+                "traffic": 396827136 + 242642944,
                 "alg_bytes_per_launch": ab, "avg_launch_ms": t_bwd,
                 "launches_timed": len(kt["msda_rows_backward"]), "timing": timer_note,
                 "sca_forward": {"avg_launch_ms": t_fwd,
@@ -423,7 +434,8 @@ def run_ours(args):
         cstep, q_per_step, _ = cpu_reference_step_factory(1, 1)
         cstep()                                       # warm-up
         t0 = time.perf_counter(); cstep(); cdt = time.perf_counter() - t0
-        cpu = {"value": q_per_step / cdt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": q_per_step / cdt, "unit": UNIT, "cores": cpu_threads(), "host_cores": os.cpu_count(),
+               "kind": "port",
                "sample": "1 of 6 encoder layers fwd+bwd on the base inputs (fp32, pure-PyTorch "
                          "restatement of the reference modules, grid_sample fallback), 1 warm-up + 1 timed; "
                          "q/s = 40000 / (6 x sample time)"}

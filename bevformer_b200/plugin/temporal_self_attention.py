@@ -10,6 +10,7 @@ bracketed by the dense projections of ``plugin/linear.py``.
 from __future__ import annotations
 
 import math
+import os
 import warnings
 
 import torch
@@ -106,7 +107,8 @@ class TemporalSelfAttention(nn.Module):
         if reference_points.shape[-1] == 2:
             ref = reference_points.reshape(bs * 2, nq, self.num_levels, 2).float().contiguous()
             lp = self.num_levels * self.num_points
-            if self.num_heads == 8 and lp in (2, 4, 8, 16, 32) and nv == nq:
+            if (self.num_heads == 8 and lp in (2, 4, 8, 16, 32) and nv == nq
+                    and os.environ.get("BEVF_TSA_INTERLEAVE", "1") != "0"):
                 # interleaved rows (b, q, frame): the sampler writes (bs*Nq, 2C) and the mean over the
                 # two frames (:257-265) is folded into the output projection as [W | W] / 2 -- no
                 # reduction kernel forward, no scatter of the gradient to the two frames backward

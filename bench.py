@@ -27,6 +27,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from bevformer_b200 import synthetic as syn  # noqa: E402
+from bevformer_b200.dist import average_gradients_flat  # noqa: E402
 
 METRIC = "BEV queries/sec (bevformer_base 200x200x256, 6 cams) fwd+bwd"
 UNIT = "BEV queries/s"
@@ -218,14 +219,8 @@ def run_ours(args):
     params = [p for p in enc.parameters()]
 
     def allreduce_grads():
-        """Data-parallel gradient averaging for the graph-replayed step: the encoder's 4.94 M
-        parameter gradients (9.9 MB in bf16) travel as ONE flat bucket through one NCCL all-reduce
-        over NVLink, then are scattered back in place.  (Eager mode uses torch DDP instead.)"""
-        grads = [p.grad for p in params]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat)
-        flat.div_(world)
-        torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
+        """Graph-replayed step: one flat-bucket NCCL all-reduce (eager mode uses torch DDP instead)."""
+        average_gradients_flat(params, world)
     # one synthetic sample per GPU (weak scaling), different per rank
     host = syn.make_encoder_inputs(w, bs=1, seed=rank)
     pin = {k: getattr(host, k).to(dtype).pin_memory()

@@ -34,9 +34,8 @@ def _worker(rank, world, port, out):
     o.square().mean().backward()
     key = "layers.0.ffns.0.layers.1.weight"
     local = sd[key].grad.clone()
-    for p in sd.values():                                       # what DDP does after backward
-        dist.all_reduce(p.grad)
-        p.grad /= world
+    from bevformer_b200.dist import average_gradients_flat
+    average_gradients_flat(list(sd.values()), world)            # bench.py's one-bucket exchange
     ms = torch.tensor([float(rank + 1)])
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)                   # bench.py's max-over-ranks timing
     gathered = [torch.zeros_like(local) for _ in range(world)]

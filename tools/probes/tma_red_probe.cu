@@ -2,7 +2,7 @@
 //   (a) REDG.E.ADD.F32x4 issued by the lanes (the sampler backward's path),
 //   (b) cp.reduce.async.bulk .add.f32 from shared memory (TMA engine),
 //   (c) both at once (half of the rows each).
-// Rows are pseudo-random 128 B-aligned addresses in a 256 MB buffer, 8 rows per warp-instruction
+// Rows are pseudo-random 128 B-aligned addresses in a buffer of 16..512 MB, 8 rows per warp-instruction
 // like the bf16 sampler.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_red_probe tma_red_probe.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(256) probe(float* buf, uint32_t rows_mask, int
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-int main() {
-    const size_t bytes = 256ull << 20;
+static int run(size_t mb) {
+    const size_t bytes = mb << 20;
+    printf("-- target buffer %zu MB\n", mb);
     float* buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
     const uint32_t mask = (uint32_t)(bytes / 128) - 1;
     const int iters = 512, grid = 148 * 8;
@@ -64,6 +65,13 @@ int main() {
         printf("%-28s %8.3f ms  %7.2f G rows/s  %6.2f TB/s payload  err=%s\n", names[mode], ms, rows / ms / 1e6,
                rows * 128 / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
     }
-    // correctness: total mass
+    cudaFree(buf);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    // buffer sizes either side of the 126 MB L2: hit-dominated vs miss-dominated reductions
+    const size_t sizes[] = {16, 32, 64, 128, 256, 512};
+    for (size_t mb : sizes) run(mb);
     return 0;
 }

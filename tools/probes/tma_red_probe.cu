@@ -11,6 +11,8 @@
 __device__ __forceinline__ uint32_t hash32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
 __device__ __forceinline__ void red4(float* p, float a) { asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" :: "l"(p), "f"(a) : "memory"); }
 
+__device__ __forceinline__ void red4_bf16x2(void* p, uint32_t a) { asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%1,%1,%1};" :: "l"(p), "r"(a) : "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(256) probe(float* buf, uint32_t rows_mask, int iters) {
     __shared__ __align__(128) float stage[8][2][8][32];            // warp, buffer, row, 32 floats
@@ -21,7 +23,9 @@ __global__ void __launch_bounds__(256) probe(float* buf, uint32_t rows_mask, int
         const uint32_t r = hash32(seed + it * 8 + grp) & rows_mask;  // row index (128 B rows)
         float* dst = buf + (size_t)r * 32;
         const bool use_tma = (MODE == 1) || (MODE == 2 && (it & 1));
-        if (!use_tma) {
+        if (MODE == 3) {                                             // same row, bf16 accumulation: 64 B per row
+            red4_bf16x2(reinterpret_cast<char*>(dst) + 16 * sub, 0x3c003c00u);
+        } else if (!use_tma) {
             red4(dst + 4 * sub, 1.0f);
             red4(dst + 16 + 4 * sub, 1.0f);
         } else {
@@ -51,13 +55,14 @@ static int run(size_t mb) {
     const uint32_t mask = (uint32_t)(bytes / 128) - 1;
     const int iters = 512, grid = 148 * 8;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const char* names[3] = {"REDG.v4 (lanes)", "cp.reduce.async.bulk (TMA)", "half / half"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char* names[4] = {"REDG.v4 (lanes)", "cp.reduce.async.bulk (TMA)", "half / half", "REDG.v4.bf16x2 (64 B rows)"};
+    for (int mode = 0; mode < 4; ++mode) {
         for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(a);
             if (mode == 0) probe<0><<<grid, 256>>>(buf, mask, iters);
             if (mode == 1) probe<1><<<grid, 256>>>(buf, mask, iters);
             if (mode == 2) probe<2><<<grid, 256>>>(buf, mask, iters);
+            if (mode == 3) probe<3><<<grid, 256>>>(buf, mask, iters);
             cudaEventRecord(b); cudaEventSynchronize(b);
         }
         float ms; cudaEventElapsedTime(&ms, a, b);

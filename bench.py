@@ -295,7 +295,7 @@ def run_ours(args):
             graph, static_loss, launches_per_replay, graph_timers = capture(True)
             graph.replay()
             torch.cuda.synchronize()
-            _ = [a.elapsed_time(b) for a, b in graph_timers["msda_rows_backward"]]
+            _ = [a.elapsed_time(b) for a, b, _t in graph_timers["msda_rows_backward"]]
         except Exception:  # noqa: BLE001 - event nodes unsupported here: capture again without them
             torch.cuda.synchronize()
             graph, static_loss, launches_per_replay, graph_timers = capture(False)
@@ -361,6 +361,12 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    def read_timers(timers):
+        """elapsed ms of the SCA launches only (tag = (rows, levels): SCA samples 4 levels over the
+        pair list, the interleaved TSA one level over 2*Nq rows)."""
+        return {k: [a.elapsed_time(b) for a, b, tag in v if tag is None or tag[1] == len(w.levels)]
+                for k, v in timers.items()}
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -376,14 +382,14 @@ def run_ours(args):
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     if graph is None:
-        kt = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.KERNEL_TIMERS.items()}
+        kt = read_timers(ops.KERNEL_TIMERS)
         timer_note = "CUDA events around every launch of the kernel inside the timed region"
     else:
         # the event pairs were captured as nodes of the graph: after the timed replays they hold the
         # kernel's duration in the LAST timed step (one sample per launch site)
         launches = launches_per_replay * args.steps
         try:
-            kt = {k: [a.elapsed_time(b) for a, b in v] for k, v in graph_timers.items()}
+            kt = read_timers(graph_timers)
             timer_note = ("CUDA event nodes captured around each launch site in the step's CUDA graph; "
                           "values are from the last timed replay")
         except Exception as exc:  # noqa: BLE001
@@ -394,7 +400,7 @@ def run_ours(args):
             for _ in range(3):
                 step({k: v.detach() for k, v in dev_in.items()})
             torch.cuda.synchronize()
-            kt = {k: [a.elapsed_time(b) for a, b in v] for k, v in ops.KERNEL_TIMERS.items()}
+            kt = read_timers(ops.KERNEL_TIMERS)
             timer_note = ("CUDA events around each launch in 3 eager replays of the same step, run right "
                           "after the timed graph replays (kernels inside a CUDA graph cannot be bracketed)")
     ops.KERNEL_TIMERS.clear()

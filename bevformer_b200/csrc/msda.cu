@@ -298,19 +298,32 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     uint4 gh = make_uint4(0, 0, 0, 0);            // the same slice as packed bf16, for FHFMA dots
     if constexpr (kHalfDot)
         gh = __ldg(reinterpret_cast<const uint4 *>(grad_out + row * 32 + sub * VEC));
-    // Scatter layout.  A 16 B reduction covers 4 fp32 channels.  With VEC == 8 the lane's own
-    // channels [8 sub, 8 sub + 8) would make each of its two reductions hit every other 16 B of the
-    // row (half-filled sectors); instead reduction r of lane `sub` takes channels
-    // [16 r + 4 sub, 16 r + 4 sub + 4), so one instruction writes 64 contiguous bytes per row.
-    constexpr int NRED = VEC / 4;
-    float gr[NRED][4];
-    if constexpr (NRED == 1) {
-        gr[0][0] = g[0]; gr[0][1] = g[1]; gr[0][2] = g[2]; gr[0][3] = g[3];
+    // Scatter layout.  A 16 B reduction covers 4 fp32 channels and the reduction path is fastest
+    // when one warp instruction fills whole 128 B lines (measured: +21 % rows/s over half lines,
+    // tools/probes/tma_red_probe.cu).  VEC == 4: the 8 lanes of a row already write its 128 B.
+    // VEC == 8 (4 lanes per row, 8 rows per warp): rows are paired (grp, grp ^ 4); instruction A
+    // fills the lines of the low rows -- their own lanes write channels [4 sub, +4), the partner's
+    // lanes write [16 + 4 sub, +4) -- and instruction B does the same for the high rows.  Each lane
+    // therefore keeps 4 grad_out channels of its own row and 4 of its partner's, and reads the
+    // partner's per-sample scalars with one extra shuffle each.
+    constexpr bool kPaired = (VEC == 8);
+    const bool hi = kPaired && (grp & 4);
+    const long long vrow = voff - sub * VEC;                       // element offset of the row in its map
+    long long vrow_a = vrow, vrow_b = vrow;
+    float gra[4], grb[4];
+    if constexpr (!kPaired) {
+        gra[0] = g[0]; gra[1] = g[1]; gra[2] = g[2]; gra[3] = g[3];
+        grb[0] = grb[1] = grb[2] = grb[3] = 0.f;
     } else {
-#pragma unroll
-        for (int r = 0; r < NRED; ++r) load_vec<TG, 4>(grad_out + row * 32 + 16 * r + 4 * sub, gr[r]);
+        const long long row_p = __shfl_xor_sync(0xffffffffu, row, 16);
+        const long long vrow_p = __shfl_xor_sync(0xffffffffu, vrow, 16);
+        const int chan = (hi ? 16 : 0) + 4 * sub;
+        const long long row_a = hi ? row_p : row, row_b = hi ? row : row_p;
+        vrow_a = (hi ? vrow_p : vrow) + chan;
+        vrow_b = (hi ? vrow : vrow_p) + chan;
+        load_vec<TG, 4>(grad_out + row_a * 32 + chan, gra);
+        load_vec<TG, 4>(grad_out + row_b * 32 + chan, grb);
     }
-    const int red_shift = (NRED == 1) ? 0 : (4 * sub - sub * VEC);   // from the lane's load offset
 
     for (int s0 = 0; s0 < LP; s0 += LANES) {
         // ---- produce
@@ -359,14 +372,41 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
                 d[j][0] = v00.dot(g); d[j][1] = v01.dot(g); d[j][2] = v10.dot(g); d[j][3] = v11.dot(g);
             }
             // scatter w * a * g with 16 B reductions; zero-weight corners are skipped
-            float *gv = grad_value + o00 + red_shift;
-#pragma unroll
-            for (int r = 0; r < NRED; ++r) {
-                float *gp = gv + 16 * r;
-                if (q00 != 0.f) red_add_v4(gp, q00 * gr[r][0], q00 * gr[r][1], q00 * gr[r][2], q00 * gr[r][3]);
-                if (q01 != 0.f) red_add_v4(gp + ox, q01 * gr[r][0], q01 * gr[r][1], q01 * gr[r][2], q01 * gr[r][3]);
-                if (q10 != 0.f) red_add_v4(gp + oy, q10 * gr[r][0], q10 * gr[r][1], q10 * gr[r][2], q10 * gr[r][3]);
-                if (q11 != 0.f) red_add_v4(gp + oy + ox, q11 * gr[r][0], q11 * gr[r][1], q11 * gr[r][2], q11 * gr[r][3]);
+            if constexpr (!kPaired) {
+                float *gp = grad_value + o00;
+                if (q00 != 0.f) red_add_v4(gp, q00 * gra[0], q00 * gra[1], q00 * gra[2], q00 * gra[3]);
+                if (q01 != 0.f) red_add_v4(gp + ox, q01 * gra[0], q01 * gra[1], q01 * gra[2], q01 * gra[3]);
+                if (q10 != 0.f) red_add_v4(gp + oy, q10 * gra[0], q10 * gra[1], q10 * gra[2], q10 * gra[3]);
+                if (q11 != 0.f) red_add_v4(gp + oy + ox, q11 * gra[0], q11 * gra[1], q11 * gra[2], q11 * gra[3]);
+            } else {
+                const int ep = __shfl_xor_sync(0xffffffffu, e, 16);
+                const float p00 = __shfl_xor_sync(0xffffffffu, q00, 16);
+                const float p01 = __shfl_xor_sync(0xffffffffu, q01, 16);
+                const float p10 = __shfl_xor_sync(0xffffffffu, q10, 16);
+                const float p11 = __shfl_xor_sync(0xffffffffu, q11, 16);
+                const int oxp = (ep & 1) ? pix : 0, oyp = (ep & 2) ? tab.rs[l] : 0;
+                {   // instruction A: lines of the low rows (own scalars on low lanes, partner's on high)
+                    const int ea = hi ? ep : e;
+                    const int xa = hi ? oxp : ox, ya = hi ? oyp : oy;
+                    const float a00 = hi ? p00 : q00, a01 = hi ? p01 : q01, a10 = hi ? p10 : q10,
+                                a11 = hi ? p11 : q11;
+                    float *gp = grad_value + vrow_a + tab.lofs[l] + (long long)((unsigned)ea & ~3u);
+                    if (a00 != 0.f) red_add_v4(gp, a00 * gra[0], a00 * gra[1], a00 * gra[2], a00 * gra[3]);
+                    if (a01 != 0.f) red_add_v4(gp + xa, a01 * gra[0], a01 * gra[1], a01 * gra[2], a01 * gra[3]);
+                    if (a10 != 0.f) red_add_v4(gp + ya, a10 * gra[0], a10 * gra[1], a10 * gra[2], a10 * gra[3]);
+                    if (a11 != 0.f) red_add_v4(gp + ya + xa, a11 * gra[0], a11 * gra[1], a11 * gra[2], a11 * gra[3]);
+                }
+                {   // instruction B: lines of the high rows
+                    const int eb = hi ? e : ep;
+                    const int xb = hi ? ox : oxp, yb = hi ? oy : oyp;
+                    const float b00 = hi ? q00 : p00, b01 = hi ? q01 : p01, b10 = hi ? q10 : p10,
+                                b11 = hi ? q11 : p11;
+                    float *gp = grad_value + vrow_b + tab.lofs[l] + (long long)((unsigned)eb & ~3u);
+                    if (b00 != 0.f) red_add_v4(gp, b00 * grb[0], b00 * grb[1], b00 * grb[2], b00 * grb[3]);
+                    if (b01 != 0.f) red_add_v4(gp + xb, b01 * grb[0], b01 * grb[1], b01 * grb[2], b01 * grb[3]);
+                    if (b10 != 0.f) red_add_v4(gp + yb, b10 * grb[0], b10 * grb[1], b10 * grb[2], b10 * grb[3]);
+                    if (b11 != 0.f) red_add_v4(gp + yb + xb, b11 * grb[0], b11 * grb[1], b11 * grb[2], b11 * grb[3]);
+                }
             }
         }
         // ---- reduce-scatter the dots over the group: lane `sub` ends with the totals of sample

@@ -17,14 +17,16 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 # bench.py's roofline needs the duration of individual launches inside the timed region: when a name
 # is present in KERNEL_TIMERS, the wrapper brackets that launch with CUDA events on the launching
-# stream and appends the pair (elapsed times are read after the region's final synchronize).
+# stream and appends (start, end, tag) -- elapsed times are read after the region's final synchronize;
+# tag = (rows, levels) of the launch, which tells the SCA launches (4 levels) from the TSA ones (1).
 KERNEL_TIMERS: dict = {}
 
 
 class _timed:
-    def __init__(self, name, device):
+    def __init__(self, name, device, tag=None):
         self.rec = KERNEL_TIMERS.get(name)
         self.device = device
+        self.tag = tag
 
     def __enter__(self):
         if self.rec is not None:
@@ -35,7 +37,7 @@ class _timed:
     def __exit__(self, *a):
         if self.rec is not None:
             self.e.record(torch.cuda.current_stream(self.device))
-            self.rec.append((self.s, self.e))
+            self.rec.append((self.s, self.e, self.tag))
 
 
 def _stream_ptr(t: torch.Tensor) -> int:
@@ -209,7 +211,7 @@ def msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_m
     out_dtype = out_dtype or value.dtype
     out = torch.empty((R, M * D), device=value.device, dtype=out_dtype)
     lib = _lib.load()
-    with torch.cuda.device(value.device), _timed("msda_rows_forward", value.device):
+    with torch.cuda.device(value.device), _timed("msda_rows_forward", value.device, (R, L)):
         st = lib.bevf_msda_rows_forward(value.data_ptr(), _DT[value.dtype], ss.data_ptr(),
                                         ls.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                                         out.data_ptr(), _DT[out_dtype], row_map.data_ptr(),
@@ -231,7 +233,7 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
     grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
     lib = _lib.load()
-    with torch.cuda.device(value.device), _timed("msda_rows_backward", value.device):
+    with torch.cuda.device(value.device), _timed("msda_rows_backward", value.device, (R, L)):
         st = lib.bevf_msda_rows_backward(value.data_ptr(), _DT[value.dtype], ss.data_ptr(),
                                          ls.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                                          grad_output.data_ptr(), _DT[grad_output.dtype],

@@ -23,7 +23,12 @@ __global__ void __launch_bounds__(256) probe(float* buf, uint32_t rows_mask, int
         const uint32_t r = hash32(seed + it * 8 + grp) & rows_mask;  // row index (128 B rows)
         float* dst = buf + (size_t)r * 32;
         const bool use_tma = (MODE == 1) || (MODE == 2 && (it & 1));
-        if (MODE == 3) {                                             // same row, bf16 accumulation: 64 B per row
+        if (MODE == 4) {                                             // full 128 B line per row per instruction
+            const int sub8 = lane & 7, g4 = lane >> 3;                 // 8 lanes per row, 4 rows per instruction
+            const uint32_t ra = hash32(seed + it * 8 + g4) & rows_mask, rb = hash32(seed + it * 8 + 4 + g4) & rows_mask;
+            red4(buf + (size_t)ra * 32 + 4 * sub8, 1.0f);
+            red4(buf + (size_t)rb * 32 + 4 * sub8, 1.0f);
+        } else if (MODE == 3) {                                             // same row, bf16 accumulation: 64 B per row
             red4_bf16x2(reinterpret_cast<char*>(dst) + 16 * sub, 0x3c003c00u);
         } else if (!use_tma) {
             red4(dst + 4 * sub, 1.0f);
@@ -55,14 +60,15 @@ static int run(size_t mb) {
     const uint32_t mask = (uint32_t)(bytes / 128) - 1;
     const int iters = 512, grid = 148 * 8;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const char* names[4] = {"REDG.v4 (lanes)", "cp.reduce.async.bulk (TMA)", "half / half", "REDG.v4.bf16x2 (64 B rows)"};
-    for (int mode = 0; mode < 4; ++mode) {
+    const char* names[5] = {"REDG.v4 (lanes)", "cp.reduce.async.bulk (TMA)", "half / half", "REDG.v4.bf16x2 (64 B rows)", "REDG.v4 full line / instr"};
+    for (int mode = 0; mode < 5; ++mode) {
         for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(a);
             if (mode == 0) probe<0><<<grid, 256>>>(buf, mask, iters);
             if (mode == 1) probe<1><<<grid, 256>>>(buf, mask, iters);
             if (mode == 2) probe<2><<<grid, 256>>>(buf, mask, iters);
             if (mode == 3) probe<3><<<grid, 256>>>(buf, mask, iters);
+            if (mode == 4) probe<4><<<grid, 256>>>(buf, mask, iters);
             cudaEventRecord(b); cudaEventSynchronize(b);
         }
         float ms; cudaEventElapsedTime(&ms, a, b);
@@ -76,7 +82,7 @@ static int run(size_t mb) {
 
 int main(int argc, char** argv) {
     // buffer sizes either side of the 126 MB L2: hit-dominated vs miss-dominated reductions
-    const size_t sizes[] = {16, 32, 64, 128, 256, 512};
+    const size_t sizes[] = {32, 256};
     for (size_t mb : sizes) run(mb);
     return 0;
 }

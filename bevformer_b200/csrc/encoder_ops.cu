@@ -58,11 +58,18 @@ sca_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref_cam,
     }
 }
 
+// scalar / pair stores into an f32 or bf16 gradient tensor
+__device__ __forceinline__ void st1(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(bf16 *p, float a, float b) { *reinterpret_cast<uint32_t *>(p) = pack_bf16x2(a, b); }
+
 // d_raw for every query: sums over the cameras that see it (pair_of[cam][q] = row or -1)
+template <typename TO>
 __global__ void __launch_bounds__(kEThreads)
 sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
              const float *__restrict__ grad_attn, const int *__restrict__ pair_of,
-             const int64_t *__restrict__ level_hw, float *__restrict__ d_raw, int B, int Nq, int R,
+             const int64_t *__restrict__ level_hw, TO *__restrict__ d_raw, int B, int Nq, int R,
              int M, int L, int P, int ncam) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Nq * M;
@@ -72,8 +79,8 @@ sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
     const int q = (int)(bq % Nq), b = (int)(bq / Nq);
     const int LP = L * P, nout = M * LP * 3;
     const float *lg = raw + bq * nout + (long long)M * LP * 2 + (long long)m * LP;
-    float *d_off = d_raw + bq * nout + (long long)m * LP * 2;
-    float *d_lg = d_raw + bq * nout + (long long)M * LP * 2 + (long long)m * LP;
+    TO *d_off = d_raw + bq * nout + (long long)m * LP * 2;
+    TO *d_lg = d_raw + bq * nout + (long long)M * LP * 2 + (long long)m * LP;
     int rows[16];
     int n = 0;
     for (int c = 0; c < ncam && c < 16; ++c) {
@@ -104,8 +111,8 @@ sca_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
                 gx += g2.x; gy += g2.y;
             }
             const float a = __expf(lg[k] - mx) * inv;
-            d_lg[k] = a * (ga - dot);
-            *reinterpret_cast<float2 *>(d_off + 2 * k) = make_float2(__fdiv_rn(gx, fw), __fdiv_rn(gy, fh));
+            st1(d_lg + k, a * (ga - dot));
+            st2(d_off + 2 * k, __fdiv_rn(gx, fw), __fdiv_rn(gy, fh));
         }
     }
 }
@@ -156,6 +163,27 @@ template <int N> __device__ __forceinline__ void stv(float *p, const float (&v)[
     }
 }
 
+// d_raw may be wanted in bf16 (it feeds the bf16 dX / dW GEMMs of the offsets|logits head): the
+// rounding then happens here instead of in a separate cast pass over the tensor
+template <int N> __device__ __forceinline__ void stv(bf16 *p, const float (&v)[N]) {
+    if constexpr (N % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 8)
+            *reinterpret_cast<uint4 *>(p + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                                                           pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+    } else if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4)
+            *reinterpret_cast<uint2 *>(p + i) = make_uint2(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]));
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) *reinterpret_cast<uint32_t *>(p + i) = pack_bf16x2(v[i], v[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+
 template <int PPL>
 __global__ void __launch_bounds__(kEThreads)
 sca_prep_fwd_m8(const float *__restrict__ raw, const float *__restrict__ ref_cam,
@@ -199,11 +227,11 @@ sca_prep_fwd_m8(const float *__restrict__ raw, const float *__restrict__ ref_cam
     stv<PPL>(attn + (t * M + m) * LP + k0, lg);
 }
 
-template <int PPL>
+template <int PPL, typename TO>
 __global__ void __launch_bounds__(kEThreads)
 sca_prep_bwd_m8(const float *__restrict__ raw, const float *__restrict__ grad_loc,
                 const float *__restrict__ grad_attn, const int *__restrict__ pair_of,
-                const int64_t *__restrict__ level_hw, float *__restrict__ d_raw, int B, int Nq, int R,
+                const int64_t *__restrict__ level_hw, TO *__restrict__ d_raw, int B, int Nq, int R,
                 int L, int P, int ncam, int pmagic) {
     constexpr int M = 8;
     __shared__ float s_w[16], s_h[16];
@@ -380,10 +408,11 @@ tsa_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref2d,
     }
 }
 
+template <typename TO>
 __global__ void __launch_bounds__(kEThreads)
 tsa_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
              const float *__restrict__ grad_attn, const int64_t *__restrict__ level_hw,
-             float *__restrict__ d_raw, int B, int Nq, int M, int L, int P) {
+             TO *__restrict__ d_raw, int B, int Nq, int M, int L, int P) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Nq * M * 2;
     if (t >= total) return;
@@ -411,9 +440,9 @@ tsa_prep_bwd(const float *__restrict__ raw, const float *__restrict__ grad_loc,
         for (int p = 0; p < P; ++p) {
             const int k = l * P + p;
             const float a = __expf(lg[k] - mx) * inv;
-            d_raw[o_lg + k] = a * (ga[k] - dot);
+            st1(d_raw + o_lg + k, a * (ga[k] - dot));
             const float2 g2 = *reinterpret_cast<const float2 *>(gl + 2 * k);
-            *reinterpret_cast<float2 *>(d_raw + o_off + 2 * k) = make_float2(__fdiv_rn(g2.x, fw), __fdiv_rn(g2.y, fh));
+            st2(d_raw + o_off + 2 * k, __fdiv_rn(g2.x, fw), __fdiv_rn(g2.y, fh));
         }
     }
 }
@@ -757,12 +786,12 @@ point_sampling_kernel(const float *__restrict__ lidar2img, PointSamplingParams p
 // queue entry j = (lane / 2) % 2, half = lane % 2); a lane owns PPL = L*P/2 points; the softmax over
 // the L*P points of one (head, queue entry) reduces over the lane pair.
 // ------------------------------------------------------------------------------------------------
-template <int PPL, bool kBackward>
+template <int PPL, bool kBackward, typename TO>
 __global__ void __launch_bounds__(kEThreads)
 tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
             const float *__restrict__ grad_loc, const float *__restrict__ grad_attn,
             const int64_t *__restrict__ level_hw, float *__restrict__ loc, float *__restrict__ attn,
-            float *__restrict__ d_raw, int B, int Nq, int L, int P, int pmagic, int interleave) {
+            TO *__restrict__ d_raw, int B, int Nq, int L, int P, int pmagic, int interleave) {
     constexpr int M = 8;
     __shared__ float s_w[16], s_h[16];
     if ((int)threadIdx.x < L) { s_h[threadIdx.x] = (float)level_hw[2 * threadIdx.x]; s_w[threadIdx.x] = (float)level_hw[2 * threadIdx.x + 1]; }
@@ -825,17 +854,17 @@ tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
     }
 }
 
-template <bool kBackward>
+template <bool kBackward, typename TO>
 static bool launch_tsa_prep_m8(const float *raw, const float *ref2d, const float *grad_loc,
                                const float *grad_attn, const int64_t *level_hw, float *loc, float *attn,
-                               float *d_raw, int B, int Nq, int M, int L, int P, int interleave,
+                               TO *d_raw, int B, int Nq, int M, int L, int P, int interleave,
                                cudaStream_t st) {
     const int LP = L * P;
     if (!(M == 8 && L <= 16 && LP * P < 65536 && (LP == 2 || LP == 4 || LP == 8 || LP == 16 || LP == 32)))
         return false;
     const int pmagic = (65536 + P - 1) / P;
     const unsigned grid = (unsigned)(((long long)B * Nq + kEThreads / 32 - 1) / (kEThreads / 32));
-#define BEVF_TSA_CASE(N) tsa_prep_m8<N, kBackward><<<grid, kEThreads, 0, st>>>(raw, ref2d, grad_loc, grad_attn, level_hw, loc, attn, d_raw, B, Nq, L, P, pmagic, interleave)
+#define BEVF_TSA_CASE(N) tsa_prep_m8<N, kBackward, TO><<<grid, kEThreads, 0, st>>>(raw, ref2d, grad_loc, grad_attn, level_hw, loc, attn, d_raw, B, Nq, L, P, pmagic, interleave)
     switch (LP / 2) {
         case 1: BEVF_TSA_CASE(1); break;
         case 2: BEVF_TSA_CASE(2); break;
@@ -883,31 +912,43 @@ extern "C" int bevf_sca_prep_forward(const float *raw, const float *ref_cam, con
     return check_launch(who);
 }
 
-extern "C" int bevf_sca_prep_backward(const float *raw, const float *grad_loc,
-                                      const float *grad_attn, const int32_t *pair_of,
-                                      const int64_t *level_hw, float *d_raw, int B, int Nq, int R,
-                                      int M, int L, int P, int ncam, void *stream) {
-    const char *who = "bevf_sca_prep_backward";
-    BEVF_REQUIRE(B >= 0 && Nq >= 0 && R >= 0 && M > 0 && L > 0 && P > 0 && ncam > 0 && ncam <= 16, who, "bad dimension (ncam <= 16)");
+template <typename TO>
+static int sca_prep_backward_t(const char *who, const float *raw, const float *grad_loc, const float *grad_attn,
+                               const int32_t *pair_of, const int64_t *level_hw, TO *d_raw, int B, int Nq,
+                               int R, int M, int L, int P, int ncam, cudaStream_t st) {
     const long long total = (long long)B * Nq * M;
-    if (total == 0) return 0;
-    BEVF_REQUIRE(raw && pair_of && level_hw && d_raw && (R == 0 || (grad_loc && grad_attn)), who, "null pointer argument");
     const int LP = L * P, pmagic = (65536 + P - 1) / P;
-    cudaStream_t st = (cudaStream_t)stream;
     const unsigned wgrid = blocks_for((long long)B * Nq, kEThreads / 32);
     if (M == 8 && L <= 16 && LP * P < 65536 && (LP == 4 || LP == 8 || LP == 16 || LP == 32 || LP == 64)) {
+#define BEVF_SCA_CASE(N) sca_prep_bwd_m8<N, TO><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic)
         switch (LP / 4) {
-            case 1: sca_prep_bwd_m8<1><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
-            case 2: sca_prep_bwd_m8<2><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
-            case 4: sca_prep_bwd_m8<4><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
-            case 8: sca_prep_bwd_m8<8><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
-            default: sca_prep_bwd_m8<16><<<wgrid, kEThreads, 0, st>>>(raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, L, P, ncam, pmagic); break;
+            case 1: BEVF_SCA_CASE(1); break;
+            case 2: BEVF_SCA_CASE(2); break;
+            case 4: BEVF_SCA_CASE(4); break;
+            case 8: BEVF_SCA_CASE(8); break;
+            default: BEVF_SCA_CASE(16); break;
         }
+#undef BEVF_SCA_CASE
     } else {
-        sca_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, st>>>(
+        sca_prep_bwd<TO><<<blocks_for(total, kEThreads), kEThreads, 0, st>>>(
             raw, grad_loc, grad_attn, pair_of, level_hw, d_raw, B, Nq, R, M, L, P, ncam);
     }
     return check_launch(who);
+}
+
+extern "C" int bevf_sca_prep_backward(const float *raw, const float *grad_loc,
+                                      const float *grad_attn, const int32_t *pair_of,
+                                      const int64_t *level_hw, void *d_raw, int out_dtype, int B, int Nq,
+                                      int R, int M, int L, int P, int ncam, void *stream) {
+    const char *who = "bevf_sca_prep_backward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && R >= 0 && M > 0 && L > 0 && P > 0 && ncam > 0 && ncam <= 16, who, "bad dimension (ncam <= 16)");
+    BEVF_REQUIRE(out_dtype == BEVF_DTYPE_F32 || out_dtype == BEVF_DTYPE_BF16, who, "unsupported dtype code");
+    if ((long long)B * Nq * M == 0) return 0;
+    BEVF_REQUIRE(raw && pair_of && level_hw && d_raw && (R == 0 || (grad_loc && grad_attn)), who, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == BEVF_DTYPE_BF16)
+        return sca_prep_backward_t<bf16>(who, raw, grad_loc, grad_attn, pair_of, level_hw, (bf16 *)d_raw, B, Nq, R, M, L, P, ncam, st);
+    return sca_prep_backward_t<float>(who, raw, grad_loc, grad_attn, pair_of, level_hw, (float *)d_raw, B, Nq, R, M, L, P, ncam, st);
 }
 
 extern "C" int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const int64_t *level_hw,
@@ -918,7 +959,7 @@ extern "C" int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const
     const long long total = (long long)B * Nq * M * 2;
     if (total == 0) return 0;
     BEVF_REQUIRE(raw && ref2d && level_hw && loc && attn, who, "null pointer argument");
-    if (!launch_tsa_prep_m8<false>(raw, ref2d, nullptr, nullptr, level_hw, loc, attn, nullptr, B, Nq, M, L, P,
+    if (!launch_tsa_prep_m8<false, float>(raw, ref2d, nullptr, nullptr, level_hw, loc, attn, nullptr, B, Nq, M, L, P,
                                    interleave, (cudaStream_t)stream)) {
         if (interleave) return fail("%s: interleaved rows need num_heads == 8 and L*P in {2,4,8,16,32}", who);
         tsa_prep_fwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
@@ -927,21 +968,33 @@ extern "C" int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const
     return check_launch(who);
 }
 
-extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
-                                      const float *grad_attn, const int64_t *level_hw, float *d_raw,
-                                      int B, int Nq, int M, int L, int P, int interleave, void *stream) {
-    const char *who = "bevf_tsa_prep_backward";
-    BEVF_REQUIRE(B >= 0 && Nq >= 0 && M > 0 && L > 0 && P > 0, who, "bad dimension");
+template <typename TO>
+static int tsa_prep_backward_t(const char *who, const float *raw, const float *grad_loc, const float *grad_attn,
+                               const int64_t *level_hw, TO *d_raw, int B, int Nq, int M, int L, int P,
+                               int interleave, cudaStream_t st) {
     const long long total = (long long)B * Nq * M * 2;
-    if (total == 0) return 0;
-    BEVF_REQUIRE(raw && grad_loc && grad_attn && level_hw && d_raw, who, "null pointer argument");
-    if (!launch_tsa_prep_m8<true>(raw, nullptr, grad_loc, grad_attn, level_hw, nullptr, nullptr, d_raw, B, Nq, M,
-                                  L, P, interleave, (cudaStream_t)stream)) {
+    if (!launch_tsa_prep_m8<true, TO>(raw, nullptr, grad_loc, grad_attn, level_hw, nullptr, nullptr, d_raw, B, Nq, M,
+                                      L, P, interleave, st)) {
         if (interleave) return fail("%s: interleaved rows need num_heads == 8 and L*P in {2,4,8,16,32}", who);
-        tsa_prep_bwd<<<blocks_for(total, kEThreads), kEThreads, 0, (cudaStream_t)stream>>>(
+        tsa_prep_bwd<TO><<<blocks_for(total, kEThreads), kEThreads, 0, st>>>(
             raw, grad_loc, grad_attn, level_hw, d_raw, B, Nq, M, L, P);
     }
     return check_launch(who);
+}
+
+extern "C" int bevf_tsa_prep_backward(const float *raw, const float *grad_loc,
+                                      const float *grad_attn, const int64_t *level_hw, void *d_raw,
+                                      int out_dtype, int B, int Nq, int M, int L, int P, int interleave,
+                                      void *stream) {
+    const char *who = "bevf_tsa_prep_backward";
+    BEVF_REQUIRE(B >= 0 && Nq >= 0 && M > 0 && L > 0 && P > 0, who, "bad dimension");
+    BEVF_REQUIRE(out_dtype == BEVF_DTYPE_F32 || out_dtype == BEVF_DTYPE_BF16, who, "unsupported dtype code");
+    if ((long long)B * Nq * M * 2 == 0) return 0;
+    BEVF_REQUIRE(raw && grad_loc && grad_attn && level_hw && d_raw, who, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == BEVF_DTYPE_BF16)
+        return tsa_prep_backward_t<bf16>(who, raw, grad_loc, grad_attn, level_hw, (bf16 *)d_raw, B, Nq, M, L, P, interleave, st);
+    return tsa_prep_backward_t<float>(who, raw, grad_loc, grad_attn, level_hw, (float *)d_raw, B, Nq, M, L, P, interleave, st);
 }
 
 template <typename T, typename TP>

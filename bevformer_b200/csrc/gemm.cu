@@ -653,6 +653,8 @@ gemm_wgrad_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 // (ncu on v1: 123 MB through L2 for 82 MB of operands, tensor pipe 14 %), and the three roles run
 // free behind mbarriers instead of meeting at a __syncthreads per unit.
 // ------------------------------------------------------------------------------------------------
+constexpr int kWgradEpiBytes = 4 * 32 * 33 * 4;            // four epilogue warps x (32 x 33) fp32 transpose tile
+constexpr int kWgradPipeBytes = 208 * 1024;                 // + 1 KB alignment + barriers + tiles <= 227 KB
 struct Wgrad2Params {
     int M, N, K;
     int BN;                // tile width along K (multiple of 64, <= 256, divides K)
@@ -679,6 +681,8 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
     uint64_t *acc_full = empty + p.stages;
     uint64_t *acc_empty = acc_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
+    // per-epilogue-warp 32 x 33 fp32 transpose tile (see the epilogue)
+    float *epi_tiles = reinterpret_cast<float *>(tmem_slot + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blocks_n = (p.N + kBM - 1) / kBM;
@@ -852,14 +856,28 @@ gemm_wgrad2_bf16(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
                                 *reinterpret_cast<float4 *>(dst + 16 * h + i) =
                                     make_float4(__uint_as_float(r[h][i]), __uint_as_float(r[h][i + 1]),
                                                 __uint_as_float(r[h][i + 2]), __uint_as_float(r[h][i + 3]));
-                    } else if (row < p.N) {
-                        float *dst = p.dw + (size_t)row * p.K + tk * p.BN + c0;
+                    } else {
+                        // A lane holds 32 consecutive columns of ONE dW row, so reducing straight from
+                        // the registers would touch 32 rows x 16 B per instruction (half-filled sectors,
+                        // ncu: 32 sectors / request).  Transpose the 32 x 32 block through shared memory
+                        // (row stride 33 words: conflict-free both ways) so that every reduction
+                        // instruction covers 4 rows x 128 contiguous bytes.
+                        float *tile = epi_tiles + q * (32 * 33);
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                red_add_v4(dst + 16 * h + i, __uint_as_float(r[h][i]), __uint_as_float(r[h][i + 1]),
-                                           __uint_as_float(r[h][i + 2]), __uint_as_float(r[h][i + 3]));
+                            for (int i = 0; i < 16; ++i) tile[lane * 33 + 16 * h + i] = __uint_as_float(r[h][i]);
+                        __syncwarp();
+                        const int rr = lane >> 3, cc = (lane & 7) * 4;
+                        const int row0 = (gn * p.NB + nb) * kBM + q * 32;
+#pragma unroll
+                        for (int ps = 0; ps < 8; ++ps) {
+                            const int rl = ps * 4 + rr;
+                            const float *src = tile + rl * 33 + cc;
+                            if (row0 + rl < p.N)
+                                red_add_v4(p.dw + (size_t)(row0 + rl) * p.K + tk * p.BN + c0 + cc, src[0], src[1], src[2], src[3]);
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -1113,11 +1131,11 @@ extern "C" int bevf_linear_wgrad(const void *dy, const void *x, float *dw, float
         splits2 = (int)((M + rows2 - 1) / rows2);
         q.rows_per_split = rows2; q.splits = splits2;
         const int stage2 = q.NB * 2 * 8192 + (bn / 64) * 8192;
-        int st2 = (216 * 1024) / stage2;
+        int st2 = (kWgradPipeBytes) / stage2;
         if (st2 > 6) st2 = 6;
         if (st2 < 2) st2 = 2;
         q.stages = st2;
-        const size_t smem2 = (size_t)st2 * stage2 + 1024 + (2 * st2 + 2) * 8 + 16;
+        const size_t smem2 = (size_t)st2 * stage2 + 1024 + (2 * st2 + 2) * 8 + 16 + kWgradEpiBytes;
         const int units2 = tiles2 * splits2;
         const int grid2 = units2 < num_sms ? units2 : num_sms;
         gemm_wgrad2_bf16<<<grid2, kGemmThreads, smem2, (cudaStream_t)stream>>>(map_dy, map_x, q);
@@ -1201,11 +1219,11 @@ extern "C" int bevf_linear_wgrad_out(const void *dy, const void *x, void *dw, vo
     if (int e = make_map_2d(&map_x, x, (uint64_t)M, (uint64_t)K, 64))
         return fail("%s: cuTensorMapEncodeTiled(X) failed (%lld)", who, e);
     const int stage = q.NB * 2 * 8192 + (q.BN / 64) * 8192;
-    int st = (216 * 1024) / stage;
+    int st = (kWgradPipeBytes) / stage;
     if (st > 6) st = 6;
     if (st < 2) st = 2;
     q.stages = st;
-    const size_t smem = (size_t)st * stage + 1024 + (2 * st + 2) * 8 + 16;
+    const size_t smem = (size_t)st * stage + 1024 + (2 * st + 2) * 8 + 16 + kWgradEpiBytes;
     const int groups = q.n_pad / (q.NB * kBM);
     const int units = groups * (K / q.BN) * q.splits;
     const int grid = units < sms ? units : sms;

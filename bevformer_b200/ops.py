@@ -275,14 +275,17 @@ def sca_prep_forward(raw, ref_cam, pair_q, pair_cam, level_hw, B, Nq, M, L, P):
     return loc, attn
 
 
-def sca_prep_backward(raw, grad_loc, grad_attn, pair_of, level_hw, B, Nq, R, M, L, P):
+def sca_prep_backward(raw, grad_loc, grad_attn, pair_of, level_hw, B, Nq, R, M, L, P,
+                      out_dtype=torch.float32):
+    """d_raw of the SCA sampling-point prep; out_dtype=bfloat16 rounds in the kernel (the result then
+    feeds the bf16 GEMMs of the head without a cast pass)."""
     ncam = pair_of.shape[0]
-    d_raw = torch.empty_like(raw)
+    d_raw = torch.empty(raw.shape, device=raw.device, dtype=out_dtype)
     lib = _lib.load()
     with torch.cuda.device(raw.device):
         st = lib.bevf_sca_prep_backward(raw.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
                                         pair_of.data_ptr(), level_hw.data_ptr(), d_raw.data_ptr(),
-                                        B, Nq, R, M, L, P, ncam, _stream_ptr(raw))
+                                        _DT[out_dtype], B, Nq, R, M, L, P, ncam, _stream_ptr(raw))
     _lib.check(st, lib)
     return d_raw
 
@@ -318,6 +321,19 @@ def tsa_prep_forward(raw, ref2d, level_hw, B, Nq, M, L, P, interleave=False):
     return loc, attn
 
 
+def tsa_prep_backward(raw, grad_loc, grad_attn, level_hw, B, Nq, M, L, P, interleave=0,
+                      out_dtype=torch.float32):
+    d_raw = torch.empty(raw.shape, device=raw.device, dtype=out_dtype)
+    lib = _lib.load()
+    with torch.cuda.device(raw.device):
+        st = lib.bevf_tsa_prep_backward(raw.data_ptr(), grad_loc.contiguous().data_ptr(),
+                                        grad_attn.contiguous().data_ptr(), level_hw.data_ptr(),
+                                        d_raw.data_ptr(), _DT[out_dtype], B, Nq, M, L, P,
+                                        int(interleave), _stream_ptr(raw))
+    _lib.check(st, lib)
+    return d_raw
+
+
 class TsaPrep(Function):
     @staticmethod
     def forward(ctx, raw, ref2d, level_hw, B, Nq, M, L, P, interleave=False):
@@ -330,13 +346,7 @@ class TsaPrep(Function):
     @once_differentiable
     def backward(ctx, grad_loc, grad_attn):
         raw, level_hw = ctx.saved_tensors
-        d_raw = torch.empty_like(raw)
-        lib = _lib.load()
-        with torch.cuda.device(raw.device):
-            st = lib.bevf_tsa_prep_backward(raw.data_ptr(), grad_loc.contiguous().data_ptr(),
-                                            grad_attn.contiguous().data_ptr(), level_hw.data_ptr(),
-                                            d_raw.data_ptr(), *ctx.dims, _stream_ptr(raw))
-        _lib.check(st, lib)
+        d_raw = tsa_prep_backward(raw, grad_loc, grad_attn, level_hw, *ctx.dims)
         return (d_raw,) + (None,) * 8
 
 

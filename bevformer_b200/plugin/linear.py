@@ -122,3 +122,70 @@ def linear_fp32_out(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor
         return _LinearTC.apply(x, weight, bias, False, True)
     y = F.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
     return y.float()
+
+
+# ---------------------------------------------------------------------------------------------------
+# offsets|logits head + sampling-point preparation as ONE autograd node.  Between the two sits the
+# (rows, M*L*P*3) fp32 tensor of raw offsets and logits; as separate nodes its gradient has to be
+# fp32 (autograd casts a gradient to the dtype of the forward output) and is then cast to bf16 for the
+# dX / dW GEMMs -- a read+write of 180 MB per layer at base.  Fused, the prep backward rounds to bf16
+# itself.
+# ---------------------------------------------------------------------------------------------------
+class _HeadTC(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, kind, prep_args):
+        w = weight.to(torch.bfloat16)
+        xc = x.contiguous()
+        raw = ops.linear_tc(xc, w, bias, None, False, torch.float32).reshape(-1, w.shape[0])
+        if kind == "sca":
+            ref_cam, pair_q, pair_cam, pair_of, ss, bs, nq, m, l, p = prep_args
+            loc, attn = ops.sca_prep_forward(raw, ref_cam, pair_q, pair_cam, ss, bs, nq, m, l, p)
+        else:
+            ref, ss, bs, nq, m, l, p, interleave = prep_args
+            loc, attn = ops.tsa_prep_forward(raw, ref, ss, bs, nq, m, l, p, interleave)
+        ctx.save_for_backward(xc, w, raw)
+        ctx.kind, ctx.prep_args = kind, prep_args
+        ctx.meta = (bias is not None, weight.dtype, None if bias is None else bias.dtype)
+        return loc, attn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loc, grad_attn):
+        x, w, raw = ctx.saved_tensors
+        has_bias, wdt, bdt = ctx.meta
+        k, n = w.shape[1], w.shape[0]
+        grad_loc, grad_attn = grad_loc.contiguous(), grad_attn.contiguous()
+        if ctx.kind == "sca":
+            _ref_cam, pair_q, _pair_cam, pair_of, ss, bs, nq, m, l, p = ctx.prep_args
+            d_raw = ops.sca_prep_backward(raw, grad_loc, grad_attn, pair_of, ss, bs, nq,
+                                          pair_q.numel(), m, l, p, out_dtype=torch.bfloat16)
+        else:
+            _ref, ss, bs, nq, m, l, p, interleave = ctx.prep_args
+            d_raw = ops.tsa_prep_backward(raw, grad_loc, grad_attn, ss, bs, nq, m, l, p, interleave,
+                                          out_dtype=torch.bfloat16)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_tc(d_raw, w.t().contiguous(), None, None, False).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw, db = _wgrad(d_raw, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None)
+        elif has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(d_raw).to(bdt)
+        return dx, dw, db, None, None
+
+
+def sca_sampling_head(x, weight, bias, ref_cam, pair_q, pair_cam, pair_of, ss, bs, nq, m, l, p):
+    """(loc, attn) of SpatialCrossAttention for the in-view (camera, query) pairs: the stacked
+    sampling_offsets|attention_weights projection followed by softmax / normalisation / anchor
+    broadcast (spatial_cross_attention.py:338-372)."""
+    if _use_tc(x, weight):
+        return _HeadTC.apply(x, weight, bias, "sca", (ref_cam, pair_q, pair_cam, pair_of, ss, bs, nq, m, l, p))
+    raw = linear_fp32_out(x, weight, bias).reshape(bs * nq, -1)
+    return ops.ScaPrep.apply(raw, ref_cam, pair_q, pair_cam, pair_of, ss, bs, nq, m, l, p)
+
+
+def tsa_sampling_head(x, weight, bias, ref, ss, bs, nq, m, l, p, interleave=False):
+    """(loc, attn) of TemporalSelfAttention (temporal_self_attention.py:199-229)."""
+    if _use_tc(x, weight):
+        return _HeadTC.apply(x, weight, bias, "tsa", (ref, ss, bs, nq, m, l, p, bool(interleave)))
+    raw = linear_fp32_out(x, weight, bias).reshape(bs * nq, -1)
+    return ops.TsaPrep.apply(raw, ref, ss, bs, nq, m, l, p, interleave)

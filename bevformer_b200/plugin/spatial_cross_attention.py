@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import linear, linear_fp32_out
+from .linear import linear, sca_sampling_head
 from .registry import ATTENTION, _register, build_attention
 from .temporal_self_attention import _check_head_dim, ring_offsets_
 
@@ -133,7 +133,6 @@ class MSDeformableAttention3D(nn.Module):
             v = v.masked_fill(key_padding_mask[..., None], 0.0)
         v = v.view(bs, nv, m, -1)
         w, b = self.head_weights()
-        raw = linear_fp32_out(query, w, b).reshape(bs * nq, -1)
         ss = torch.as_tensor(spatial_shapes).to(device=query.device, dtype=torch.int64)
         lsi = torch.as_tensor(level_start_index).to(device=query.device, dtype=torch.int64)
         d = reference_points.shape[2]
@@ -143,8 +142,8 @@ class MSDeformableAttention3D(nn.Module):
         pair_q = torch.arange(nq, device=dev, dtype=torch.int32)
         pair_cam = torch.zeros(nq, device=dev, dtype=torch.int32)
         pair_of = pair_q.view(1, nq).contiguous()
-        loc, attn = ops.ScaPrep.apply(raw, ref, pair_q, pair_cam, pair_of, ss.contiguous(), bs, nq,
-                                      m, l, p)
+        loc, attn = sca_sampling_head(query, w, b, ref, pair_q, pair_cam, pair_of, ss.contiguous(),
+                                      bs, nq, m, l, p)
         out = ops.MultiScaleDeformableAttnFunction_fp32.apply(
             v, ss, lsi, loc.view(bs, nq, m, l, p, 2), attn.view(bs, nq, m, l, p), self.im2col_step)
         return out if self.batch_first else out.permute(1, 0, 2)
@@ -191,9 +190,8 @@ class SpatialCrossAttention(nn.Module):
             raise AssertionError("num_points must be a multiple of the pillar anchors")   # :369
         # offsets / logits once per BEV query: they do not depend on the camera (:338-341)
         w, b = da.head_weights()
-        raw = linear_fp32_out(query, w, b).reshape(bs * nq, -1)
-        loc, attn = ops.ScaPrep.apply(raw, plan.ref_cam, plan.pair_q, plan.pair_cam, plan.pair_of,
-                                      ss, bs, nq, m, l, p)
+        loc, attn = sca_sampling_head(query, w, b, plan.ref_cam, plan.pair_q, plan.pair_cam,
+                                      plan.pair_of, ss, bs, nq, m, l, p)
         # value_proj over every camera's feature pyramid (:334), batch-major like the reference
         feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s, c)
         v = linear(feats, da.value_proj.weight, da.value_proj.bias).view(bs * ncam, s, m, -1)

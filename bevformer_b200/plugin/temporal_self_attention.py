@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import linear, linear_fp32_out
+from .linear import linear, linear_fp32_out, tsa_sampling_head
 from .registry import ATTENTION, _register
 
 
@@ -100,7 +100,6 @@ class TemporalSelfAttention(nn.Module):
         v = v.reshape(bs * 2, nv, self.num_heads, -1)
         w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
         b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
-        raw = linear_fp32_out(q_cat, w, b).reshape(bs * nq, -1)
 
         ss = torch.as_tensor(spatial_shapes).to(device=query.device, dtype=torch.int64)
         lsi = torch.as_tensor(level_start_index).to(device=query.device, dtype=torch.int64)
@@ -112,14 +111,15 @@ class TemporalSelfAttention(nn.Module):
                 # interleaved rows (b, q, frame): the sampler writes (bs*Nq, 2C) and the mean over the
                 # two frames (:257-265) is folded into the output projection as [W | W] / 2 -- no
                 # reduction kernel forward, no scatter of the gradient to the two frames backward
-                loc, attn = ops.TsaPrep.apply(raw, ref, ss.contiguous(), bs, nq, self.num_heads,
+                loc, attn = tsa_sampling_head(q_cat, w, b, ref, ss.contiguous(), bs, nq, self.num_heads,
                                               self.num_levels, self.num_points, True)
                 out = ops.SamplerRows.apply(v, loc, attn, self._frame_map(bs, nq, query.device), ss, lsi)
                 w2 = torch.cat([self.output_proj.weight, self.output_proj.weight], 1) * 0.5
                 return linear(out.view(bs, nq, 2 * c), w2, self.output_proj.bias)
-            loc, attn = ops.TsaPrep.apply(raw, ref, ss.contiguous(), bs, nq, self.num_heads,
+            loc, attn = tsa_sampling_head(q_cat, w, b, ref, ss.contiguous(), bs, nq, self.num_heads,
                                           self.num_levels, self.num_points)
         elif reference_points.shape[-1] == 4:
+            raw = linear_fp32_out(q_cat, w, b).reshape(bs * nq, -1)
             loc, attn = self._box_points(raw, reference_points, bs, nq)
         else:
             raise ValueError(f"Last dim of reference_points must be 2 or 4, "

@@ -140,11 +140,12 @@ BEVF_API int bevf_sca_prep_forward(const float *raw, const float *ref_cam, const
                                    float *attn, int B, int Nq, int R, int M, int L, int P, int D,
                                    int ncam, void *stream);
 
-/* Backward of the above into d_raw (B*Nq, M*L*P*3) f32, fully overwritten; pair_of (ncam, Nq) int32
- * holds the pair row of (camera, query) or -1. */
+/* Backward of the above into d_raw (B*Nq, M*L*P*3), fully overwritten, stored as out_dtype (f32, or
+ * bf16 when it feeds the bf16 dX / dW GEMMs of the head directly); pair_of (ncam, Nq) int32 holds the
+ * pair row of (camera, query) or -1. */
 BEVF_API int bevf_sca_prep_backward(const float *raw, const float *grad_loc, const float *grad_attn,
-                                    const int32_t *pair_of, const int64_t *level_hw, float *d_raw,
-                                    int B, int Nq, int R, int M, int L, int P, int ncam,
+                                    const int32_t *pair_of, const int64_t *level_hw, void *d_raw,
+                                    int out_dtype, int B, int Nq, int R, int M, int L, int P, int ncam,
                                     void *stream);
 
 /*
@@ -161,9 +162,10 @@ BEVF_API int bevf_tsa_prep_forward(const float *raw, const float *ref2d, const i
                                    float *loc, float *attn, int B, int Nq, int M, int L, int P,
                                    int interleave, void *stream);
 
+/* d_raw (B*Nq, M*2*L*P*3) stored as out_dtype (f32 or bf16), fully overwritten. */
 BEVF_API int bevf_tsa_prep_backward(const float *raw, const float *grad_loc, const float *grad_attn,
-                                    const int64_t *level_hw, float *d_raw, int B, int Nq, int M,
-                                    int L, int P, int interleave, void *stream);
+                                    const int64_t *level_hw, void *d_raw, int out_dtype, int B, int Nq,
+                                    int M, int L, int P, int interleave, void *stream);
 
 /*
  * y = LayerNorm(dropout(x) + residual) * gamma + beta, optionally also y_plus_pos = y + pos.

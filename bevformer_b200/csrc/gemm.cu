@@ -309,7 +309,11 @@ struct GemmWsParams {
     const void *bias;      // (N) f32 or bf16, or null
     int bias_bf16;
     int out_f32;
+    int b_mn;              // 0: B = weight (N, K) row-major, K-major tiles (Y = X W^T)
+                           // 1: B = (K, N) row-major, MN-major tiles (Y = X B; dX = dY W without W^T)
 };
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t chunk_bytes);
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -375,8 +379,15 @@ gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int tn = 0; tn < tiles_n; ++tn) {
                 mbar_wait(b_empty, (uint32_t)((tn & 1) ^ 1));         // previous column block fully consumed
                 mbar_expect_tx(b_full, (uint32_t)b_bytes);
-                for (int kb = 0; kb < kblocks; ++kb)
-                    tma_load_2d(smem_b + (size_t)kb * b_kb_bytes, &map_b, b_full, kb * kBK, tn * p.BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (!p.b_mn) {
+                        tma_load_2d(smem_b + (size_t)kb * b_kb_bytes, &map_b, b_full, kb * kBK, tn * p.BN);
+                    } else {                       // 64 reduction rows x BN columns as BN/64 chunks of 8 KB
+                        for (int c = 0; c < p.BN / 64; ++c)
+                            tma_load_2d(smem_b + (size_t)kb * b_kb_bytes + c * 8192, &map_b, b_full,
+                                        tn * p.BN + c * 64, kb * kBK);
+                    }
+                }
                 for (int tm = blockIdx.x; tm < tiles_m; tm += gridDim.x) {
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(&empty[s], ph ^ 1);
@@ -390,7 +401,7 @@ gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(kBM, p.BN);
+            const uint32_t idesc = instr_desc_bf16(kBM, p.BN) | (p.b_mn ? (1u << 16) : 0u);
             int s = 0; uint32_t ph = 0;
             int as = 0; uint32_t aph = 0;
             for (int tn = 0; tn < tiles_n; ++tn) {
@@ -405,10 +416,13 @@ gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
                         const uint64_t da = smem_desc_k_sw128(smem_u32(smem_a + (size_t)s * a_bytes));
-                        const uint64_t db = smem_desc_k_sw128(b_addr + (uint32_t)(kb * b_kb_bytes));
+                        // K-major B: 16 k-columns further = 32 B; MN-major B: 16 k-rows = 2048 B
+                        const uint64_t db = p.b_mn ? smem_desc_mn_sw128(b_addr + (uint32_t)(kb * b_kb_bytes), 8192)
+                                                   : smem_desc_k_sw128(b_addr + (uint32_t)(kb * b_kb_bytes));
+                        const uint64_t db_step = p.b_mn ? 128 : 2;
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k)
-                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + db_step * (uint64_t)k, idesc,
                                       (uint32_t)((kb | k) != 0));
                         umma_commit(&empty[s]);
                         if (kb == kblocks - 1) umma_commit(&acc_full[as]);
@@ -991,9 +1005,57 @@ static int pick_bn(int N) {
     return 0;
 }
 
+// weight-stationary launch shared by the forward projection (b_mn = 0, B = W (N, K)) and the input
+// gradient (b_mn = 1, B = W (K_red, N_out) read in place)
+static int launch_ws(const char *who, const void *x, const void *b, const void *bias, int bias_dtype, void *y,
+                     bool f32, int64_t M, int N, int K, int bn_ws, int relu, int b_mn, void *stream) {
+    CUtensorMap map_a, map_b, map_y;
+    if (int e = make_map_2d(&map_a, x, (uint64_t)M, (uint64_t)K, kBM))
+        return fail("%s: cuTensorMapEncodeTiled(A) failed (%lld)", who, e);
+    if (int e = b_mn ? make_map_2d(&map_b, b, (uint64_t)K, (uint64_t)N, 64)
+                     : make_map_2d(&map_b, b, (uint64_t)N, (uint64_t)K, (uint32_t)bn_ws))
+        return fail("%s: cuTensorMapEncodeTiled(B) failed (%lld)", who, e);
+    if (int e = make_map_out(&map_y, y, (uint64_t)M, (uint64_t)N, f32))
+        return fail("%s: cuTensorMapEncodeTiled(Y) failed (%lld)", who, e);
+    GemmWsParams q;
+    q.M = (int)M; q.N = N; q.K = K; q.BN = bn_ws; q.relu = relu; q.bias = bias;
+    q.bias_bf16 = bias_dtype == BEVF_DTYPE_BF16; q.out_f32 = f32 ? 1 : 0; q.b_mn = b_mn;
+    const int b_bytes = ((bn_ws * K * 2) + 1023) & ~1023;
+    int stages = (227 * 1024 - 1024 - b_bytes - 32 * 1024 - 1024 - 256) / (kBM * 128);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return fail("%s: not enough shared memory for the A ring", who);
+    q.stages = stages;
+    const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * kBM * 128 + 32 * 1024 + 1024 + 256;
+    static int sms_ws = 0;
+    if (sms_ws == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms_ws, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gemm_nt_ws_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    const int tiles_m = (int)((M + kBM - 1) / kBM);
+    const int grid = tiles_m < sms_ws ? tiles_m : sms_ws;
+    gemm_nt_ws_bf16<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, q);
+    return check_launch(who);
+}
+
 }  // namespace bevf
 
 using namespace bevf;
+
+extern "C" int bevf_linear_dgrad(const void *dy, const void *w, void *dx, int64_t M, int N, int K, void *stream) {
+    const char *who = "bevf_linear_dgrad";
+    if (M < 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
+    if (M == 0) return 0;
+    if (!dy || !w || !dx) return fail("%s: null pointer argument", who);
+    if (N % kBK != 0 || K % 64 != 0) return fail("%s: N and K must be multiples of 64 (got %lld, %lld)", who, N, K);
+    if (M >= (1ll << 31)) return fail("%s: M too large", who);
+    if (!aligned16(dy) || !aligned16(w) || !aligned16(dx)) return fail("%s: pointers must be 16-byte aligned", who);
+    // output columns = K of the weight, reduction = its N rows
+    const int bn = pick_bn_ws(K, N, 64);
+    if (bn == 0) return fail("%s: no 64-column tile of the weight fits shared memory", who);
+    return launch_ws(who, dy, w, nullptr, BEVF_DTYPE_F32, dx, false, M, K, N, bn, 0, 1, stream);
+}
 
 extern "C" int bevf_linear_forward(const void *x, const void *w, const void *bias, int bias_dtype,
                                    const void *residual, void *y, int y_dtype, int64_t M, int N, int K,
@@ -1018,35 +1080,8 @@ extern "C" int bevf_linear_forward(const void *x, const void *w, const void *bia
     }
     const bool f32 = y_dtype == BEVF_DTYPE_F32;
     const int bn_ws = pick_bn_ws(N, K, f32 ? 32 : 64);
-    if (use_ws && !residual && bn_ws > 0) {
-        CUtensorMap map_a, map_b, map_y;
-        if (int e = make_map_2d(&map_a, x, (uint64_t)M, (uint64_t)K, kBM))
-            return fail("%s: cuTensorMapEncodeTiled(A) failed (%lld)", who, e);
-        if (int e = make_map_2d(&map_b, w, (uint64_t)N, (uint64_t)K, (uint32_t)bn_ws))
-            return fail("%s: cuTensorMapEncodeTiled(B) failed (%lld)", who, e);
-        if (int e = make_map_out(&map_y, y, (uint64_t)M, (uint64_t)N, f32))
-            return fail("%s: cuTensorMapEncodeTiled(Y) failed (%lld)", who, e);
-        GemmWsParams q;
-        q.M = (int)M; q.N = N; q.K = K; q.BN = bn_ws; q.relu = relu; q.bias = bias;
-        q.bias_bf16 = bias_dtype == BEVF_DTYPE_BF16; q.out_f32 = f32 ? 1 : 0;
-        const int b_bytes = ((bn_ws * K * 2) + 1023) & ~1023;
-        int stages = (227 * 1024 - 1024 - b_bytes - 32 * 1024 - 1024 - 256) / (kBM * 128);
-        if (stages > 6) stages = 6;
-        if (stages < 2) return fail("%s: not enough shared memory for the A ring", who);
-        q.stages = stages;
-        const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * kBM * 128 + 32 * 1024 + 1024 + 256;
-        static int sms_ws = 0;
-        if (sms_ws == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms_ws, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(gemm_nt_ws_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        }
-        const int tiles_m = (int)((M + kBM - 1) / kBM);
-        const int grid = tiles_m < sms_ws ? tiles_m : sms_ws;
-        gemm_nt_ws_bf16<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, q);
-        return check_launch(who);
-    }
+    if (use_ws && !residual && bn_ws > 0)
+        return launch_ws(who, x, w, bias, bias_dtype, y, f32, M, N, K, bn_ws, relu, 0, stream);
     const int bn = pick_bn(N);
     if (bn == 0) return fail("%s: no tile width divides N", who);
 

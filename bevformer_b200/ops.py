@@ -7,6 +7,8 @@ the current stream only; all arithmetic happens in ``libbevformer_b200.so``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.autograd.function import Function, once_differentiable
 
@@ -521,9 +523,30 @@ def linear_tc(x, weight, bias=None, residual=None, relu=False, out_dtype=None):
     return y
 
 
-def linear_wgrad_tc(dy, x, with_bias=False):
+def linear_dgrad_tc(dy, weight):
+    """dx = dy @ weight on the tcgen05 GEMM, the weight (N, K) read in place (no transposed copy).
+    dy (M, N) bf16 -> (M, K) bf16.  N or K not a multiple of 64: falls back to the transposed-copy form."""
+    _need_cuda(dy, "dy")
+    if dy.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or dy.shape[-1] != weight.shape[0]:
+        raise RuntimeError("linear_dgrad_tc: dy (M,N) and weight (N,K) must be bfloat16")
+    N, K = weight.shape
+    if N % 64 or K % 64 or os.environ.get("BEVF_DGRAD", "mn") == "copy":
+        return linear_tc(dy, weight.t().contiguous())
+    dy = dy.contiguous()
+    w = weight.contiguous()
+    M = dy.numel() // N
+    dx = torch.empty(dy.shape[:-1] + (K,), device=dy.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    with torch.cuda.device(dy.device):
+        st = lib.bevf_linear_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, N, K, _stream_ptr(dy))
+    _lib.check(st, lib)
+    return dx
+
+
+def linear_wgrad_tc(dy, x, with_bias=False, out_dtype=None):
     """dW = dy^T @ x on the tcgen05 split-M kernel (and db = column sums of dy from the same pass).
-    dy (M, N) bf16, x (M, K) bf16 -> (N, K) fp32 [, (N,) fp32]."""
+    dy (M, N) bf16, x (M, K) bf16 -> (N, K) fp32 [, (N,) fp32].  The kernel accumulates in one fp32
+    buffer holding [dW | db]; ``out_dtype`` converts that buffer once (dW and db are views of it)."""
     _need_cuda(dy, "dy")
     _need_cuda(x, "x")
     if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.shape[0] != x.shape[0]:
@@ -539,6 +562,10 @@ def linear_wgrad_tc(dy, x, with_bias=False):
         st = lib.bevf_linear_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _ptr(db), M, N, K,
                                    _stream_ptr(x))
     _lib.check(st, lib)
+    if out_dtype is not None and out_dtype != torch.float32:
+        buf = buf.to(out_dtype)
+        dw = buf[: N * K].view(N, K)
+        db = buf[N * K: N * K + N] if with_bias else None
     return (dw, db) if with_bias else dw
 
 

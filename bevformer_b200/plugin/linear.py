@@ -46,7 +46,7 @@ class _LinearTC(Function):
         dy2 = dy2.to(torch.bfloat16).contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear_tc(dy2, w.t().contiguous(), None, None, False).view(x.shape)
+            dx = ops.linear_dgrad_tc(dy2, w).view(x.shape)
         if ctx.needs_input_grad[1]:
             dw, db = _wgrad(dy2, x.reshape(-1, k), n, k, ctx.dtypes[0],
                             ctx.dtypes[1] if ctx.has_bias else None)
@@ -62,7 +62,9 @@ def _wgrad(dy2, x2, n, k, wdtype, bdtype=None):
         return ops.linear_wgrad_out(dy2, x2, wdtype, bdtype is not None)
     if mode != "cublas" and n % 8 == 0:
         if bdtype is None:
-            return ops.linear_wgrad_tc(dy2, x2).to(wdtype), None
+            return ops.linear_wgrad_tc(dy2, x2, out_dtype=wdtype), None
+        if bdtype == wdtype:                               # one conversion pass for [dW | db]
+            return ops.linear_wgrad_tc(dy2, x2, with_bias=True, out_dtype=wdtype)
         dw, db = ops.linear_wgrad_tc(dy2, x2, with_bias=True)
         return dw.to(wdtype), db.to(bdtype)
     dw = torch.mm(dy2.t(), x2).to(wdtype)
@@ -92,7 +94,7 @@ class _LinearReluDropoutTC(Function):
         dz = ops.relu_dropout_backward(dy.reshape(-1, n), h.reshape(-1, n), p)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear_tc(dz, w.t().contiguous(), None, None, False).view(x.shape)
+            dx = ops.linear_dgrad_tc(dz, w).view(x.shape)
         if ctx.needs_input_grad[1]:
             dw, db = _wgrad(dz, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None)
         elif has_bias and ctx.needs_input_grad[2]:
@@ -165,7 +167,7 @@ class _HeadTC(Function):
                                           out_dtype=torch.bfloat16)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.linear_tc(d_raw, w.t().contiguous(), None, None, False).view(x.shape)
+            dx = ops.linear_dgrad_tc(d_raw, w).view(x.shape)
         if ctx.needs_input_grad[1]:
             dw, db = _wgrad(d_raw, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None)
         elif has_bias and ctx.needs_input_grad[2]:

@@ -234,6 +234,15 @@ BEVF_API int bevf_linear_forward(const void *x, const void *w, const void *bias,
                                  int relu, void *stream);
 
 /*
+ * Input gradient of a projection: dx (M, K) bf16 = dy (M, N) bf16 . w (N, K) bf16 -- the
+ * `grad_input = grad_output.mm(weight)` half of F.linear's backward.  Same weight-stationary tcgen05
+ * kernel as bevf_linear_forward, but the weight is read in place as an MN-major operand (no W^T copy).
+ * N and K must be multiples of 64.
+ */
+BEVF_API int bevf_linear_dgrad(const void *dy, const void *w, void *dx, int64_t M, int N, int K,
+                               void *stream);
+
+/*
  * Weight gradient of the projection above:  dw[N,K] += dy[M,N]^T . x[M,K]   (fp32, ACCUMULATED
  * INTO: the caller zero-fills).  dy, x bf16 row-major; split over the M rows across the SMs, partial
  * tiles combined with 16 B fp32 reductions.  replaces the cuBLAS call autograd makes for

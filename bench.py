@@ -425,8 +425,8 @@ def run_ours(args):
                 "achieved": ab / t_bwd / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": ab / t_bwd / 1e6 / peak, "peak_source": peak_src,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
-                # `ncu --set full` capture profiles/r1e_ncu_full_msda_bwd_raw.csv (same kernel build)
-                "traffic": 396827136 + 242642944,
+                # `ncu --set full` capture profiles/r1p_ncu_full_msda_bwd_raw.csv (same kernel build)
+                "traffic": 396693504 + 245205504,
                 "alg_bytes_per_launch": ab, "avg_launch_ms": t_bwd,
                 "launches_timed": len(kt["msda_rows_backward"]), "timing": timer_note,
                 "sca_forward": {"avg_launch_ms": t_fwd,

@@ -391,10 +391,12 @@ def _param_ptr(p, act_dtype):
 
 class LayerNormResidual(Function):
     """y = LayerNorm(dropout_p(x) + residual) * gamma + beta (fp32 statistics); residual may be None.
-    The dropout keep-mask is regenerated from a Philox seed in backward (nothing stored)."""
+    The dropout keep-mask is regenerated from a Philox seed in backward (nothing stored).
+    With ``pos`` the kernel also writes y + pos (the next block's positional-encoded query) and the
+    call returns (y, y + pos); their two gradients are summed inside the backward kernel."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, eps, drop_p=0.0):
+    def forward(ctx, x, residual, gamma, beta, eps, drop_p=0.0, pos=None):
         _need_cuda(x, "x")
         if x.dtype not in _DT:
             raise RuntimeError("layernorm: float32 or bfloat16 only")
@@ -406,42 +408,52 @@ class LayerNormResidual(Function):
         if pd != pd2:
             g, b, pd = g.float(), b.float(), F32
         y = torch.empty_like(x)
+        y2 = None
+        if pos is not None:
+            if pos.dtype != x.dtype or pos.numel() != x.numel():
+                raise RuntimeError("layernorm: pos must match x in dtype and size")
+            pos = pos.contiguous()
+            y2 = torch.empty_like(x)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
         seed = _next_seed() if drop_p > 0.0 else 0
         sbase = seed_state(x.device) if drop_p > 0.0 else None
         lib = _lib.load()
         with torch.cuda.device(x.device):
-            st = lib.bevf_layernorm_forward(x.data_ptr(), _ptr(rc), g.data_ptr(), b.data_ptr(), pd, 0,
-                                            y.data_ptr(), 0, mean.data_ptr(), rstd.data_ptr(), rows, C,
-                                            float(eps), float(drop_p), seed, _ptr(sbase), _DT[x.dtype],
-                                            _stream_ptr(x))
+            st = lib.bevf_layernorm_forward(x.data_ptr(), _ptr(rc), g.data_ptr(), b.data_ptr(), pd,
+                                            _ptr(pos), y.data_ptr(), _ptr(y2), mean.data_ptr(),
+                                            rstd.data_ptr(), rows, C, float(eps), float(drop_p), seed,
+                                            _ptr(sbase), _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         ctx.save_for_backward(x, rc, g, mean, rstd)
-        ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed)
-        return y
+        ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed, pos is not None)
+        return y if pos is None else (y, y2)
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy2=None):
         x, res, g, mean, rstd = ctx.saved_tensors
-        has_res, gdt, bdt, pd, drop_p, seed = ctx.meta
+        has_res, gdt, bdt, pd, drop_p, seed, has_pos = ctx.meta
         C = x.shape[-1]
         rows = x.numel() // C
+        if dy is None:                                   # only y + pos was used downstream
+            dy, dy2 = dy2, None
         dy = dy.contiguous()
+        dy2 = None if dy2 is None else dy2.contiguous()
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (has_res and drop_p > 0.0) else None
         dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(x.device):
             st = lib.bevf_layernorm_backward(x.data_ptr(), _ptr(res), g.data_ptr(), pd, mean.data_ptr(),
-                                             rstd.data_ptr(), dy.data_ptr(), 0, dx.data_ptr(), _ptr(dres),
-                                             dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C, drop_p, seed,
+                                             rstd.data_ptr(), dy.data_ptr(), _ptr(dy2), dx.data_ptr(),
+                                             _ptr(dres), dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C,
+                                             drop_p, seed,
                                              _ptr(seed_state(x.device)) if drop_p > 0.0 else 0,
                                              _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         d_res = None if not has_res else (dres if dres is not None else dx)
-        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None
+        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None
 
 
 class ScaCombine(Function):

@@ -82,11 +82,12 @@ class FFN(nn.Module):
 _register(FEEDFORWARD_NETWORK, FFN, name="FFN")
 
 
-def _fused_norm(norm: nn.LayerNorm, x, residual, dropout: Optional[nn.Dropout] = None):
+def _fused_norm(norm: nn.LayerNorm, x, residual, dropout: Optional[nn.Dropout] = None, pos=None):
     """LayerNorm(dropout(x) + residual) in one kernel (fp32 statistics; the dropout of the block
-    that produced x is applied inside, active only in training mode)."""
+    that produced x is applied inside, active only in training mode).  With ``pos`` the kernel also
+    emits y + pos and the call returns (y, y + pos)."""
     p = dropout.p if (dropout is not None and dropout.training) else 0.0
-    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps, p)
+    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps, p, pos)
 
 
 class MyCustomBaseTransformerLayer(nn.Module):
@@ -211,6 +212,10 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
         order = self.operation_order
         ni = ai = fi = 0
         identity = query
+        # encoder-internal: {"q_in": query + bev_pos computed by the previous layer's last LayerNorm,
+        # "emit": write this layer's output + bev_pos there for the next layer}
+        carry = kwargs.pop("pos_carry", None)
+        q_in0 = carry.pop("q_in", None) if carry is not None else None     # valid for THIS layer's input only
         tsa_ss = kwargs.pop("tsa_spatial_shapes", None)
         tsa_lsi = kwargs.pop("tsa_level_start_index", None)
         if tsa_ss is None:                                    # (the reference rebuilds these per call)
@@ -223,8 +228,9 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
             if op == "self_attn":
                 att = self.attentions[ai]
                 if fuse and isinstance(att, TemporalSelfAttention) and att.batch_first:
+                    q_in = q_in0 if i == 0 else None
                     pre = att.attend(query, prev_bev, bev_pos, query_key_padding_mask, ref_2d,
-                                     tsa_ss, tsa_lsi)
+                                     tsa_ss, tsa_lsi, q_in=q_in)
                     query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1
@@ -256,8 +262,14 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
             elif op == "ffn":
                 ffn = self.ffns[fi]
                 if fuse and isinstance(ffn, FFN) and ffn.add_identity:
-                    query = _fused_norm(self.norms[ni], ffn.transform(query), query,
-                                        ffn.layers[ffn.num_fcs])
+                    emit = (carry is not None and carry.get("emit") and i + 2 == len(order)
+                            and bev_pos is not None and bev_pos.dtype == query.dtype)
+                    out = _fused_norm(self.norms[ni], ffn.transform(query), query,
+                                      ffn.layers[ffn.num_fcs], bev_pos if emit else None)
+                    if emit:
+                        query, carry["q_in"] = out
+                    else:
+                        query = out
                     ni += 1
                     i += 1
                 else:
@@ -411,12 +423,21 @@ class BEVFormerEncoder(nn.Module):
         lsi = torch.as_tensor(level_start_index).to(device=dev, dtype=torch.int64).contiguous()
 
         inter = []
-        for layer in self.layers:
+        # the last LayerNorm of layer i also writes (output + bev_pos), the query the temporal
+        # self-attention of layer i+1 starts from: no separate add forward, and the two gradients of
+        # the output are summed inside the LayerNorm backward kernel
+        carry = {} if (dev.type == "cuda" and not self.pre_norm) else None
+        for li, layer in enumerate(self.layers):
+            if carry is not None:
+                carry["emit"] = li + 1 < len(self.layers) and isinstance(layer, BEVFormerLayer)
+                if not isinstance(layer, BEVFormerLayer):
+                    carry.pop("q_in", None)
+            extra = dict(pos_carry=carry) if isinstance(layer, BEVFormerLayer) else {}
             query = layer(query, key, value, *args, bev_pos=pos, ref_2d=hybrid, ref_3d=None,
                           bev_h=bev_h, bev_w=bev_w, spatial_shapes=ss, level_start_index=lsi,
                           reference_points_cam=ref_cam, bev_mask=bev_mask, prev_bev=queue,
                           sca_plan=plan, tsa_spatial_shapes=tsa_ss, tsa_level_start_index=tsa_lsi,
-                          **kwargs)
+                          **extra, **kwargs)
             if self.return_intermediate:
                 inter.append(query)
         return torch.stack(inter) if self.return_intermediate else query

@@ -83,15 +83,17 @@ class TemporalSelfAttention(nn.Module):
 
     # -------------------------------------------------------------------------------------------
     def attend(self, query, value=None, query_pos=None, key_padding_mask=None,
-               reference_points=None, spatial_shapes=None, level_start_index=None):
+               reference_points=None, spatial_shapes=None, level_start_index=None, q_in=None):
         """Everything up to and including output_proj, batch-first, WITHOUT dropout / identity.
-        query (bs, Nq, C); value (bs*2, Nq, C) stacked [prev, cur] or None."""
+        query (bs, Nq, C); value (bs*2, Nq, C) stacked [prev, cur] or None; ``q_in`` = query +
+        query_pos when the caller already has it (the encoder's previous LayerNorm emits it)."""
         assert self.num_bev_queue == 2
         bs, nq, c = query.shape
         if value is None:   # first frame: the queue is the current BEV twice (:177-180)
             value = torch.stack([query, query], 1).reshape(bs * 2, nq, c)
         nv = value.shape[1]
-        q_in = query if query_pos is None else query + query_pos
+        if q_in is None:
+            q_in = query if query_pos is None else query + query_pos
         # quirk 6: the first bs rows of the stacked queue, whatever they are for bs > 1 (:197)
         q_cat = torch.cat([value[:bs], q_in], -1)
         v = linear(value, self.value_proj.weight, self.value_proj.bias)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "bevf_sca_combine_backward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "bevf_linear_forward": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 2
                             + [c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "bevf_flatten_feats": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "bevf_linear_dgrad": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_void_p]),
     "bevf_linear_wgrad": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_void_p]),
     "bevf_linear_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),

@@ -256,15 +256,25 @@ sca_prep_bwd_m8(const float *__restrict__ raw, const float *__restrict__ grad_lo
     float ga[PPL], gl[2 * PPL];
 #pragma unroll
     for (int i = 0; i < PPL; ++i) { ga[i] = 0.f; gl[2 * i] = 0.f; gl[2 * i + 1] = 0.f; }
-    for (int c = 0; c < ncam; ++c) {
-        const int r = __ldg(pair_of + (long long)c * Nq + q);          // warp-uniform
-        if (r < 0) continue;
-        const long long s = (((long long)b * R + r) * M + m) * LP + k0;
-        float t1[PPL], t2[2 * PPL];
-        ldv<PPL>(grad_attn + s, t1);
-        ldv<2 * PPL>(grad_loc + 2 * s, t2);
+    // pair rows of this query under every camera, fetched up front: the loads are independent, whereas
+    // "load row id -> test -> load gradients" per camera would serialise ncam round trips (a query is
+    // seen by 1.1 cameras on average, so most of them only find out that there is nothing to add)
+    constexpr int kCamBatch = 8;
+    for (int c0 = 0; c0 < ncam; c0 += kCamBatch) {
+        int rid[kCamBatch];
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) { ga[i] += t1[i]; gl[2 * i] += t2[2 * i]; gl[2 * i + 1] += t2[2 * i + 1]; }
+        for (int c = 0; c < kCamBatch; ++c)
+            rid[c] = (c0 + c < ncam) ? __ldg(pair_of + (long long)(c0 + c) * Nq + q) : -1;   // warp-uniform
+#pragma unroll
+        for (int c = 0; c < kCamBatch; ++c) {
+            if (rid[c] < 0) continue;
+            const long long s = (((long long)b * R + rid[c]) * M + m) * LP + k0;
+            float t1[PPL], t2[2 * PPL];
+            ldv<PPL>(grad_attn + s, t1);
+            ldv<2 * PPL>(grad_loc + 2 * s, t2);
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) { ga[i] += t1[i]; gl[2 * i] += t2[2 * i]; gl[2 * i + 1] += t2[2 * i + 1]; }
+        }
     }
     float dot = 0.f;
 #pragma unroll
@@ -854,6 +864,56 @@ tsa_prep_m8(const float *__restrict__ raw, const float *__restrict__ ref2d,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Camera features of one pyramid level, (bs, ncam, C, h*w) as the backbone/FPN emits them, into the
+// encoder's (ncam, S, bs, C) layout with the camera and level embeddings added on the way
+// (PerceptionTransformer.get_bev_features, transformer.py:161-181: flatten, permute, two broadcast
+// adds, cat over the levels, permute = five passes over the 95 MB tensor at base; here one).
+// 32 x 32 tiles through shared memory: reads run along h*w, writes along C.
+// The two adds round like the reference's tensor adds (embedding cast to T, sum rounded to T).
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float round_to(float v);
+template <> __device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_to<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+flatten_feats_kernel(const T *__restrict__ feat, const float *__restrict__ cams_embeds,
+                     const float *__restrict__ level_embed, T *__restrict__ out, int bs, int ncam, int C,
+                     int hw, int S, int level_start) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int b = blockIdx.z / ncam, cam = blockIdx.z % ncam;
+    const T *in = feat + ((long long)(b * ncam + cam) * C) * hw;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, p = p0 + tx;
+        if (c < C && p < hw) tile[ty + 8 * k][tx] = to_f<T>(in[(long long)c * hw + p]);
+    }
+    __syncthreads();
+    const int c = c0 + tx;
+    if (c >= C) return;
+    const float ce = cams_embeds ? round_to<T>(cams_embeds[cam * C + c]) : 0.f;
+    const float le = round_to<T>(level_embed[c]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = p0 + ty + 8 * k;
+        if (p >= hw) continue;
+        float v = tile[tx][ty + 8 * k];
+        if (cams_embeds) v = round_to<T>(v + ce);
+        v = v + le;
+        out[(((long long)cam * S + level_start + p) * bs + b) * C + c] = from_f<T>(v);
+    }
+}
+
 template <bool kBackward, typename TO>
 static bool launch_tsa_prep_m8(const float *raw, const float *ref2d, const float *grad_loc,
                                const float *grad_attn, const int64_t *level_hw, float *loc, float *attn,
@@ -1137,6 +1197,25 @@ extern "C" int bevf_point_sampling(const float *lidar2img, const float *pc_range
     return check_launch(who);
 }
 
+extern "C" int bevf_flatten_feats(const void *feat, const float *cams_embeds, const float *level_embed,
+                                  void *out, int bs, int ncam, int C, int hw, int S, int level_start,
+                                  int dtype, void *stream) {
+    const char *who = "bevf_flatten_feats";
+    BEVF_REQUIRE(bs >= 0 && ncam > 0 && C > 0 && hw >= 0 && S >= 0 && level_start >= 0, who, "bad dimension");
+    BEVF_REQUIRE(level_start + hw <= S, who, "the level does not fit the flattened pyramid");
+    BEVF_REQUIRE((long long)bs * ncam <= 65535, who, "bs * ncam exceeds the grid limit");
+    if ((long long)bs * hw == 0) return 0;
+    BEVF_REQUIRE(feat && level_embed && out, who, "null pointer argument");
+    const dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)(bs * ncam));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BEVF_DTYPE_F32)
+        flatten_feats_kernel<float><<<grid, 256, 0, st>>>((const float *)feat, cams_embeds, level_embed, (float *)out, bs, ncam, C, hw, S, level_start);
+    else if (dtype == BEVF_DTYPE_BF16)
+        flatten_feats_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)feat, cams_embeds, level_embed, (bf16 *)out, bs, ncam, C, hw, S, level_start);
+    else
+        return fail("%s: unsupported dtype code", who);
+    return check_launch(who);
+}
 
 extern "C" int bevf_colsum(const void *x, float *out, int64_t rows, int C, int dtype, void *stream) {
     const char *who = "bevf_colsum";

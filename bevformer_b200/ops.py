@@ -638,3 +638,55 @@ def relu_dropout_backward(dy, h, p):
                                             1.0 / (1.0 - p), _DT[dy.dtype], _stream_ptr(dy))
     _lib.check(st, lib)
     return out
+
+
+class FlattenFeats(Function):
+    """Multi-level camera features [(bs, ncam, C, h, w)] -> (ncam, S, bs, C) with cams_embeds and
+    level_embeds added (PerceptionTransformer.get_bev_features, transformer.py:161-181): one kernel
+    per level instead of flatten / permute / add / add / cat / permute.  Call as
+    ``FlattenFeats.apply(cams_embeds_or_None, level_embeds, *mlvl_feats)``."""
+
+    @staticmethod
+    def forward(ctx, cams_embeds, level_embeds, *feats):
+        f0 = feats[0]
+        _need_cuda(f0, "mlvl_feats[0]")
+        if f0.dtype not in _DT:
+            raise RuntimeError("flatten_feats: float32 or bfloat16 only")
+        bs, ncam, C = f0.shape[:3]
+        hws = [int(f.shape[3] * f.shape[4]) for f in feats]
+        S = sum(hws)
+        out = torch.empty((ncam, S, bs, C), device=f0.device, dtype=f0.dtype)
+        ce = None if cams_embeds is None else cams_embeds.detach().float().contiguous()
+        le = level_embeds.detach().float().contiguous()
+        lib = _lib.load()
+        start = 0
+        with torch.cuda.device(f0.device):
+            for lvl, f in enumerate(feats):
+                if f.dtype != f0.dtype or tuple(f.shape[:3]) != (bs, ncam, C):
+                    raise RuntimeError("flatten_feats: levels disagree in dtype / (bs, ncam, C)")
+                fc = f.contiguous()
+                st = lib.bevf_flatten_feats(fc.data_ptr(), _ptr(ce), le[lvl].data_ptr(), out.data_ptr(),
+                                            bs, ncam, C, hws[lvl], S, start, _DT[f0.dtype],
+                                            _stream_ptr(f0))
+                _lib.check(st, lib)
+                start += hws[lvl]
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.meta = (None if cams_embeds is None else cams_embeds.dtype, level_embeds.dtype)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        # data movement only (the transposes back to NCHW and three small reductions): torch ops
+        cdt, ldt = ctx.meta
+        need = ctx.needs_input_grad
+        d_cams = dy.sum((1, 2), dtype=torch.float32).to(cdt) if (cdt is not None and need[0]) else None
+        d_lvl, d_feats, start = [], [], 0
+        for i, (bs, ncam, C, h, w) in enumerate(ctx.shapes):
+            sl = dy[:, start:start + h * w]                          # (ncam, hw, bs, C)
+            if need[1]:
+                d_lvl.append(sl.sum((0, 1, 2), dtype=torch.float32))
+            d_feats.append(sl.permute(2, 0, 3, 1).reshape(bs, ncam, C, h, w) if need[2 + i] else None)
+            start += h * w
+        d_level = torch.stack(d_lvl).to(ldt) if need[1] else None
+        return (d_cams, d_level, *d_feats)

@@ -55,6 +55,17 @@ except Exception:  # noqa: BLE001
     TRANSFORMER_LAYER_SEQUENCE = Registry("transformer-layers sequence")
 
 
+# PerceptionTransformer registers in mmdet's TRANSFORMER registry (modules/transformer.py:26)
+try:  # pragma: no cover - mmdet is absent from the build image
+    from mmdet.models.utils.builder import TRANSFORMER
+except Exception:  # noqa: BLE001
+    if HAVE_MMCV:
+        from mmcv.utils import Registry as _MmcvRegistry
+        TRANSFORMER = _MmcvRegistry("Transformer")
+    else:
+        TRANSFORMER = Registry("Transformer")
+
+
 def _register(registry, cls, name=None):
     """Register without tripping over a name mmcv (or an earlier import) already holds."""
     try:
@@ -80,4 +91,6 @@ def build_transformer_layer(cfg, default_args=None):
 
 
 def build_transformer_layer_sequence(cfg, default_args=None):
+    if cfg is None:
+        return None
     return build_from_cfg(cfg, TRANSFORMER_LAYER_SEQUENCE, default_args)

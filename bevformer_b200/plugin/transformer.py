@@ -1,0 +1,142 @@
+"""PerceptionTransformer.get_bev_features on the B200 encoder.
+
+Drop-in for the BEV half of the reference class of the same name
+(projects/mmdet3d_plugin/bevformer/modules/transformer.py:26-200): same constructor arguments,
+parameter names (``level_embeds``, ``cams_embeds``, ``reference_points``, ``can_bus_mlp.*``,
+``encoder.*``) and ``get_bev_features`` signature / return value.  The object-query decoder half of the
+reference ``forward`` (transformer.py:203-289) is outside this library's scope:
+``forward`` says so instead of silently doing something else.
+
+What changes underneath: the five tensor passes that build the encoder's key/value tensor become one
+kernel per pyramid level (``bevf_flatten_feats``), and the encoder is ``plugin.encoder.BEVFormerEncoder``.
+The once-per-frame host arithmetic (ego-motion shift, CAN-bus MLP on an 18-vector, torchvision's
+nearest-neighbour rotation of prev_bev) stays as the reference wrote it.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .registry import TRANSFORMER, _register, build_transformer_layer_sequence
+
+
+class PerceptionTransformer(nn.Module):
+    def __init__(self, num_feature_levels=4, num_cams=6, two_stage_num_proposals=300, encoder=None,
+                 decoder=None, embed_dims=256, rotate_prev_bev=True, use_shift=True, use_can_bus=True,
+                 can_bus_norm=True, use_cams_embeds=True, rotate_center=[100, 100], init_cfg=None,
+                 **kwargs):
+        super().__init__()
+        self.init_cfg = init_cfg
+        self.encoder = build_transformer_layer_sequence(encoder)
+        self.decoder = None
+        self.decoder_cfg = decoder          # kept for inspection; not built (out of scope)
+        self.embed_dims = embed_dims
+        self.num_feature_levels = num_feature_levels
+        self.num_cams = num_cams
+        self.fp16_enabled = False
+        self.rotate_prev_bev = rotate_prev_bev
+        self.use_shift = use_shift
+        self.use_can_bus = use_can_bus
+        self.can_bus_norm = can_bus_norm
+        self.use_cams_embeds = use_cams_embeds
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.rotate_center = rotate_center
+        self.init_layers()
+        self.init_weights()
+
+    def init_layers(self):
+        c = self.embed_dims
+        self.level_embeds = nn.Parameter(torch.empty(self.num_feature_levels, c))
+        self.cams_embeds = nn.Parameter(torch.empty(self.num_cams, c))
+        self.reference_points = nn.Linear(c, 3)
+        self.can_bus_mlp = nn.Sequential(nn.Linear(18, c // 2), nn.ReLU(inplace=True),
+                                         nn.Linear(c // 2, c), nn.ReLU(inplace=True))
+        if self.can_bus_norm:
+            self.can_bus_mlp.add_module("norm", nn.LayerNorm(c))
+
+    def init_weights(self):
+        """transformer.py:86-101: xavier for matrices, the attention modules' own initialisers,
+        N(0,1) embeddings."""
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            init = getattr(m, "init_weight", None) or (getattr(m, "init_weights", None) if m is not self else None)
+            if init is not None and type(m).__name__ in ("MSDeformableAttention3D", "TemporalSelfAttention"):
+                init()
+        nn.init.normal_(self.level_embeds)
+        nn.init.normal_(self.cams_embeds)
+        nn.init.xavier_uniform_(self.reference_points.weight)
+        nn.init.zeros_(self.reference_points.bias)
+        for m in self.can_bus_mlp:
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    # ---------------------------------------------------------------------------------------------
+    def _shift(self, img_metas, bev_h, bev_w, grid_length):
+        """Ego-motion shift in normalised BEV units, float64 on the host exactly like the reference
+        (transformer.py:122-140)."""
+        dx = np.array([m["can_bus"][0] for m in img_metas])
+        dy = np.array([m["can_bus"][1] for m in img_metas])
+        ego = np.array([m["can_bus"][-2] / np.pi * 180 for m in img_metas])
+        length = np.sqrt(dx ** 2 + dy ** 2)
+        bev_angle = ego - np.arctan2(dy, dx) / np.pi * 180
+        sy = length * np.cos(bev_angle / 180 * np.pi) / grid_length[0] / bev_h
+        sx = length * np.sin(bev_angle / 180 * np.pi) / grid_length[1] / bev_w
+        return np.stack([sx * self.use_shift, sy * self.use_shift], -1)
+
+    def _rotate_prev(self, prev_bev, img_metas, bev_h, bev_w):
+        """prev_bev (Nq, bs, C) rotated by each sample's yaw delta (transformer.py:142-153).  Unlike
+        the reference, the caller's tensor is left untouched (the result is a new tensor)."""
+        from torchvision.transforms.functional import rotate
+        out = torch.empty_like(prev_bev)
+        for i in range(prev_bev.shape[1]):
+            img = prev_bev[:, i].reshape(bev_h, bev_w, -1).permute(2, 0, 1)
+            img = rotate(img, img_metas[i]["can_bus"][-1], center=self.rotate_center)
+            out[:, i] = img.permute(1, 2, 0).reshape(bev_h * bev_w, -1)
+        return out
+
+    def get_bev_features(self, mlvl_feats, bev_queries, bev_h, bev_w, grid_length=[0.512, 0.512],
+                         bev_pos=None, prev_bev=None, **kwargs):
+        """mlvl_feats: per level (bs, num_cams, C, h, w); bev_queries (Nq, C); bev_pos
+        (bs, C, bev_h, bev_w); prev_bev (bs, Nq, C) / (Nq, bs, C) / None; kwargs carry ``img_metas``.
+        Returns bev_embed (bs, Nq, C)."""
+        img_metas = kwargs["img_metas"]
+        bs = mlvl_feats[0].size(0)
+        bev_queries = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+        bev_pos = bev_pos.flatten(2).permute(2, 0, 1)
+        shift = bev_queries.new_tensor(self._shift(img_metas, bev_h, bev_w, grid_length))
+        if prev_bev is not None:
+            if prev_bev.shape[1] == bev_h * bev_w:
+                prev_bev = prev_bev.permute(1, 0, 2)
+            if self.rotate_prev_bev:
+                prev_bev = self._rotate_prev(prev_bev, img_metas, bev_h, bev_w)
+        can_bus = bev_queries.new_tensor([m["can_bus"] for m in img_metas])
+        can_bus = self.can_bus_mlp(can_bus)[None, :, :]
+        bev_queries = bev_queries + can_bus * self.use_can_bus
+
+        shapes = [tuple(f.shape[-2:]) for f in mlvl_feats]
+        if mlvl_feats[0].is_cuda:
+            feat_flatten = ops.FlattenFeats.apply(self.cams_embeds if self.use_cams_embeds else None,
+                                                  self.level_embeds, *mlvl_feats)
+        else:
+            raise RuntimeError("PerceptionTransformer.get_bev_features: CUDA tensors required "
+                               "(bevformer_b200 has no CPU path)")
+        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=bev_pos.device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)),
+                                       spatial_shapes.prod(1).cumsum(0)[:-1]))
+        return self.encoder(bev_queries, feat_flatten, feat_flatten, bev_h=bev_h, bev_w=bev_w,
+                            bev_pos=bev_pos, spatial_shapes=spatial_shapes,
+                            level_start_index=level_start_index, prev_bev=prev_bev, shift=shift,
+                            **kwargs)
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(
+            "bevformer_b200.PerceptionTransformer covers get_bev_features (the BEV encoder half); the "
+            "object-query decoder of the reference forward (transformer.py:203-289) is out of scope")
+
+
+_register(TRANSFORMER, PerceptionTransformer)

@@ -123,11 +123,23 @@ def make_lidar2img(scale: float = 1.0, num_cams: int = 6) -> np.ndarray:
     return np.stack(mats)
 
 
+def make_can_bus(sample: int) -> list:
+    """18 deterministic CAN-bus values in the layout the reference reads (transformer.py:122-150,
+    datasets/nuscenes_dataset.py): [0:3] ego translation delta (m), [-2] ego yaw (rad), [-1] yaw
+    delta (deg) -- the angle prev_bev is rotated by."""
+    g = np.random.default_rng(1234 + sample)
+    cb = g.standard_normal(18) * 0.1
+    cb[0], cb[1], cb[2] = 0.8 + 0.3 * sample, -0.35 + 0.2 * sample, 0.0
+    cb[-2] = 0.6 - 0.25 * sample
+    cb[-1] = 3.5 - 5.0 * sample
+    return [float(x) for x in cb]
+
+
 def make_img_metas(w: Workload, bs: int = 1):
     l2i = make_lidar2img(w.scale, w.num_cams)
     h, wd = w.img_hw
     return [dict(lidar2img=[l2i[i].copy() for i in range(w.num_cams)],
-                 img_shape=[(h, wd, 3)] * w.num_cams) for _ in range(bs)]
+                 img_shape=[(h, wd, 3)] * w.num_cams, can_bus=make_can_bus(i)) for i in range(bs)]
 
 
 @dataclass
@@ -176,6 +188,54 @@ def make_encoder_inputs(w: Workload, bs: int = 1, seed: int = 0, with_prev: bool
     return EncoderInputs(cv(bev_query), cv(feat), cv(bev_pos), cv(prev_bev),
                          shift.to(device=device, dtype=dtype), ss.to(device), lsi.to(device),
                          make_img_metas(w, bs), w.bev_h, w.bev_w)
+
+
+@dataclass
+class PerceptionInputs:
+    """Input contract of PerceptionTransformer.get_bev_features (modules/transformer.py:103-113)."""
+    mlvl_feats: list                 # per level (bs, num_cams, C, h, w)
+    bev_queries: torch.Tensor        # (Nq, C)   the BEV embedding table
+    bev_pos: torch.Tensor            # (bs, C, bev_h, bev_w)
+    prev_bev: Optional[torch.Tensor]  # (bs, Nq, C) or None
+    img_metas: list = field(default_factory=list)
+    bev_h: int = 0
+    bev_w: int = 0
+
+
+def make_perception_inputs(w: Workload, bs: int = 1, seed: int = 0, with_prev: bool = True,
+                           dtype=torch.float32, device="cpu") -> PerceptionInputs:
+    g = torch.Generator().manual_seed(4000 + seed)
+    c = w.embed_dims
+    feats = [torch.randn(bs, w.num_cams, c, h, ww, generator=g) for h, ww in w.levels]
+    bev_queries = torch.randn(w.num_query, c, generator=g)
+    bev_pos = torch.rand(bs, c, w.bev_h, w.bev_w, generator=g)
+    prev = torch.randn(bs, w.num_query, c, generator=g) if with_prev else None
+
+    def cv(t):
+        return None if t is None else t.to(device=device, dtype=dtype).contiguous()
+
+    return PerceptionInputs([cv(f) for f in feats], cv(bev_queries), cv(bev_pos), cv(prev),
+                            make_img_metas(w, bs), w.bev_h, w.bev_w)
+
+
+def make_perception_state_dict(w: Workload, seed: int = 0, trained_like: bool = True):
+    """state_dict of a PerceptionTransformer without decoder: the transformer's own parameters
+    (reference key names, modules/transformer.py:70-84) + ``encoder.*``."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    c = w.embed_dims
+    sd = {"level_embeds": torch.randn(len(w.levels), c, generator=g),
+          "cams_embeds": torch.randn(w.num_cams, c, generator=g),
+          "reference_points.weight": torch.randn(3, c, generator=g) * 0.05,
+          "reference_points.bias": torch.zeros(3),
+          "can_bus_mlp.0.weight": torch.randn(c // 2, 18, generator=g) * 0.2,
+          "can_bus_mlp.0.bias": torch.randn(c // 2, generator=g) * 0.05,
+          "can_bus_mlp.2.weight": torch.randn(c, c // 2, generator=g) * 0.1,
+          "can_bus_mlp.2.bias": torch.randn(c, generator=g) * 0.05,
+          "can_bus_mlp.norm.weight": 1.0 + 0.1 * torch.randn(c, generator=g),
+          "can_bus_mlp.norm.bias": 0.1 * torch.randn(c, generator=g)}
+    for k, v in make_state_dict(w, seed, trained_like).items():
+        sd["encoder." + k] = v
+    return sd
 
 
 def randomize_trained_like(module: torch.nn.Module, seed: int = 1) -> None:

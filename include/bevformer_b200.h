@@ -208,6 +208,17 @@ BEVF_API int bevf_sca_combine_backward(const void *g_slots, const int32_t *pair_
                                        int C, int dtype, void *stream);
 
 /*
+ * One pyramid level of camera features into the encoder's key/value layout, embeddings added.
+ * replaces PerceptionTransformer.get_bev_features' flatten / permute / +cams_embeds / +level_embeds /
+ * cat / permute (transformer.py:161-181).
+ *   feat (bs, ncam, C, hw) T in;  cams_embeds (ncam, C) f32 or null;  level_embed (C) f32;
+ *   out (ncam, S, bs, C) T: rows [level_start, level_start + hw) of every camera are written.
+ */
+BEVF_API int bevf_flatten_feats(const void *feat, const float *cams_embeds, const float *level_embed,
+                                void *out, int bs, int ncam, int C, int hw, int S, int level_start,
+                                int dtype, void *stream);
+
+/*
  * Projection of the pillar anchors into every camera + in-view mask, fp32 without FMA contraction.
  * replaces BEVFormerEncoder.get_reference_points(dim='3d') + point_sampling (encoder.py:46-71,
  * 88-149), including the 61 MB repeated-matrix materialisation.

@@ -229,3 +229,80 @@ def encoder_forward(sd: Dict[str, Tensor], num_layers: int, bev_query: Tensor, f
         if return_intermediate:
             inter.append(q)
     return torch.stack(inter) if return_intermediate else q
+
+
+# ------------------------------------------------------------------------------------------------
+# PerceptionTransformer.get_bev_features (modules/transformer.py:103-200): the encoder's caller
+# ------------------------------------------------------------------------------------------------
+def bev_shift(img_metas, bev_h: int, bev_w: int, grid_length, use_shift: bool = True):
+    """Ego-motion shift of the BEV grid in normalised units, (bs, 2) float64 numpy (xy).
+    transformer.py:122-140: translation length / heading from can_bus[0:2] and can_bus[-2]."""
+    import numpy as np
+    dx = np.array([m["can_bus"][0] for m in img_metas])
+    dy = np.array([m["can_bus"][1] for m in img_metas])
+    ego = np.array([m["can_bus"][-2] / np.pi * 180 for m in img_metas])
+    length = np.sqrt(dx ** 2 + dy ** 2)
+    ang = np.arctan2(dy, dx) / np.pi * 180
+    bev_angle = ego - ang
+    sy = length * np.cos(bev_angle / 180 * np.pi) / grid_length[0] / bev_h
+    sx = length * np.sin(bev_angle / 180 * np.pi) / grid_length[1] / bev_w
+    return np.stack([sx * use_shift, sy * use_shift], -1)
+
+
+def rotate_prev_bev(prev_bev: Tensor, img_metas, bev_h: int, bev_w: int, rotate_center) -> Tensor:
+    """prev_bev (Nq, bs, C) rotated per sample by can_bus[-1] degrees about rotate_center with
+    torchvision's nearest-neighbour ``rotate`` (transformer.py:142-153).  Returns a NEW tensor (the
+    reference writes into its argument)."""
+    from torchvision.transforms.functional import rotate
+    out = prev_bev.clone()
+    for i in range(prev_bev.shape[1]):
+        angle = img_metas[i]["can_bus"][-1]
+        img = prev_bev[:, i].reshape(bev_h, bev_w, -1).permute(2, 0, 1)
+        img = rotate(img, angle, center=rotate_center)
+        out[:, i] = img.permute(1, 2, 0).reshape(bev_h * bev_w, -1)
+    return out
+
+
+def flatten_feats(mlvl_feats, cams_embeds: Optional[Tensor], level_embeds: Tensor):
+    """(cam, S, bs, C) camera features + embeddings and the pyramid's shapes (transformer.py:161-181)."""
+    flat, shapes = [], []
+    for lvl, feat in enumerate(mlvl_feats):
+        h, w = feat.shape[-2:]
+        f = feat.flatten(3).permute(1, 0, 3, 2)                           # (cam, bs, hw, C)
+        if cams_embeds is not None:
+            f = f + cams_embeds[:, None, None, :].to(f.dtype)
+        f = f + level_embeds[None, None, lvl:lvl + 1, :].to(f.dtype)
+        flat.append(f)
+        shapes.append((h, w))
+    ss = torch.as_tensor(shapes, dtype=torch.long)
+    lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+    return torch.cat(flat, 2).permute(0, 2, 1, 3), ss, lsi
+
+
+def get_bev_features(sd: Dict[str, Tensor], num_layers: int, mlvl_feats, bev_queries: Tensor, bev_h: int,
+                     bev_w: int, *, grid_length=(0.512, 0.512), bev_pos: Tensor, prev_bev: Optional[Tensor],
+                     img_metas, rotate_center=(100, 100), rotate_prev=True, use_shift=True,
+                     use_can_bus=True, can_bus_norm=True, use_cams_embeds=True, **encoder_kwargs) -> Tensor:
+    """Functional PerceptionTransformer.get_bev_features (eval mode); ``sd`` holds the transformer's
+    parameters with ``encoder.*`` for the encoder.  Returns (bs, Nq, C)."""
+    dtype = bev_queries.dtype
+    bs = mlvl_feats[0].shape[0]
+    q = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+    pos = bev_pos.flatten(2).permute(2, 0, 1)
+    shift = torch.as_tensor(bev_shift(img_metas, bev_h, bev_w, grid_length, use_shift)).to(dtype)
+    if prev_bev is not None:
+        if prev_bev.shape[1] == bev_h * bev_w:                            # (bs, Nq, C) -> (Nq, bs, C)
+            prev_bev = prev_bev.permute(1, 0, 2)
+        if rotate_prev:
+            prev_bev = rotate_prev_bev(prev_bev, img_metas, bev_h, bev_w, list(rotate_center))
+    cb = torch.tensor([m["can_bus"] for m in img_metas], dtype=dtype)       # new_tensor: caller dtype
+    h = torch.relu(F.linear(cb, sd["can_bus_mlp.0.weight"], sd["can_bus_mlp.0.bias"]))
+    h = torch.relu(F.linear(h, sd["can_bus_mlp.2.weight"], sd["can_bus_mlp.2.bias"]))
+    if can_bus_norm:
+        h = F.layer_norm(h, (h.shape[-1],), sd["can_bus_mlp.norm.weight"], sd["can_bus_mlp.norm.bias"])
+    q = q + h[None] * use_can_bus
+    feat, ss, lsi = flatten_feats(mlvl_feats, sd["cams_embeds"] if use_cams_embeds else None,
+                                  sd["level_embeds"])
+    return encoder_forward(sd, num_layers, q, feat, bev_h=bev_h, bev_w=bev_w, bev_pos=pos,
+                           spatial_shapes=ss, level_start_index=lsi, prev_bev=prev_bev, shift=shift,
+                           img_metas=img_metas, prefix="encoder.", **encoder_kwargs)

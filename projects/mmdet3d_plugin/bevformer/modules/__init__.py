@@ -3,3 +3,4 @@ from .spatial_cross_attention import SpatialCrossAttention, MSDeformableAttentio
 from .temporal_self_attention import TemporalSelfAttention
 from .encoder import BEVFormerEncoder, BEVFormerLayer
 from .custom_base_transformer_layer import MyCustomBaseTransformerLayer
+from .transformer import PerceptionTransformer

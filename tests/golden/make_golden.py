@@ -114,6 +114,47 @@ def encoder_case(name, workload, bs=1, with_prev=True, seed=0, keep_rows=512, ba
     print(f"encoder_{name}: out {tuple(out.shape)} in {time.time() - t0:.1f}s")
 
 
+def grid_length_of(w):
+    """BEV cell size that keeps the 102.4 m range at this BEV resolution."""
+    return (0.512 * 200 / w.bev_h, 0.512 * 200 / w.bev_w)
+
+
+def perception_case(name, workload, bs=2, with_prev=True, seed=0, keep_rows=512):
+    """PerceptionTransformer.get_bev_features of the reference's own class (fp32, eval mode)."""
+    w = syn.WORKLOADS[workload]
+    PT = mmcv_stub.load_reference_transformer()
+    cfg = (mmcv_stub.load_reference_encoder_cfg(w.config_file) if w.config_file
+           else syn.encoder_cfg(w))
+    m = PT(num_feature_levels=len(w.levels), num_cams=w.num_cams, encoder=cfg, decoder=None,
+           embed_dims=w.embed_dims, rotate_center=[w.bev_h // 2, w.bev_w // 2]).eval()
+    m.load_state_dict(syn.make_perception_state_dict(w, seed=seed))
+    inp = syn.make_perception_inputs(w, bs=bs, seed=seed, with_prev=with_prev)
+    for f in inp.mlvl_feats:
+        f.requires_grad_(True)
+    inp.bev_queries.requires_grad_(True)
+    t0 = time.time()
+    prev = None if inp.prev_bev is None else inp.prev_bev.clone()      # the reference rotates in place
+    out = m.get_bev_features(inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w,
+                             grid_length=grid_length_of(w), bev_pos=inp.bev_pos, prev_bev=prev,
+                             img_metas=inp.img_metas)
+    (out * fixed_projection(out.shape)).sum().backward()
+    rq = row_subset(w.num_query, keep_rows)
+    save = dict(out_rows=out.detach()[:, rq].numpy(), out_stats=stats(out), rows_q=rq,
+                grad_queries_rows=inp.bev_queries.grad[rq].numpy(),
+                grad_queries_stats=stats(inp.bev_queries.grad))
+    for i, f in enumerate(inp.mlvl_feats):
+        save[f"grad_feat{i}_stats"] = stats(f.grad)
+        save[f"grad_feat{i}_slice"] = f.grad[:, :, :8, :2].numpy()
+    for k, p in m.named_parameters():
+        if k.startswith("encoder.") or p.grad is None:
+            continue
+        save["gstat:" + k] = stats(p.grad)
+        save["gfull:" + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"perception_{name}.npz"),
+                        meta=np.array([bs, int(with_prev), seed], dtype=np.int64), **save)
+    print(f"perception_{name}: out {tuple(out.shape)} in {time.time() - t0:.1f}s")
+
+
 def main(which):
     if not mmcv_stub.reference_available():
         raise SystemExit("needs /root/reference (dev container only)")
@@ -140,6 +181,11 @@ def main(which):
         "enc_small": lambda: encoder_case("small", "small", keep_rows=256),
         "enc_small4": lambda: encoder_case("small4", "small4", keep_rows=256),
         "enc_base": lambda: encoder_case("base", "base", keep_rows=256),
+        # PerceptionTransformer.get_bev_features: CAN-bus shift / MLP, prev_bev rotation, level + camera
+        # embeddings, then the encoder
+        "per_toy": lambda: perception_case("toy", "toy", bs=2),
+        "per_toy_noprev": lambda: perception_case("toy_noprev", "toy", bs=1, with_prev=False),
+        "per_tiny": lambda: perception_case("tiny", "tiny", bs=1, keep_rows=256),
     }
     for k in (which or cases):
         cases[k]()

@@ -163,3 +163,64 @@ def test_rig_hit_counts():
     _, mask = torch_ref.point_sampling(ref3d, syn.PC_RANGE, syn.make_img_metas(w))
     hits = [(mask[i, 0].sum(-1) > 0).sum().item() for i in range(6)]
     assert hits == [6071, 7481, 7417, 9507, 7049, 6986]
+
+
+# ---- PerceptionTransformer.get_bev_features (first "next" row) -----------------------
+PER_CASES = [("toy", "toy", 2, True), ("toy_noprev", "toy", 1, False), ("tiny", "tiny", 1, True)]
+
+
+def _grid_length(w):
+    return (0.512 * 200 / w.bev_h, 0.512 * 200 / w.bev_w)
+
+
+def _per_restatement(w, inp, sd):
+    return torch_ref.get_bev_features(sd, w.num_layers, inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w,
+                                      grid_length=_grid_length(w), bev_pos=inp.bev_pos,
+                                      prev_bev=inp.prev_bev, img_metas=inp.img_metas,
+                                      rotate_center=(w.bev_h // 2, w.bev_w // 2),
+                                      tsa_points=w.tsa_points, sca_points=w.sca_points)
+
+
+@pytest.mark.parametrize("name,workload,bs,with_prev", PER_CASES)
+def test_perception_restatement_matches_golden(name, workload, bs, with_prev):
+    g = golden("perception_" + name)
+    w = syn.WORKLOADS[workload]
+    inp = syn.make_perception_inputs(w, bs=bs, with_prev=with_prev)
+    sd = {k: v.clone().requires_grad_(True) for k, v in syn.make_perception_state_dict(w).items()}
+    for f in inp.mlvl_feats:
+        f.requires_grad_(True)
+    inp.bev_queries.requires_grad_(True)
+    prev0 = None if inp.prev_bev is None else inp.prev_bev.clone()
+    out = _per_restatement(w, inp, sd)
+    assert max_err(out[:, g["rows_q"]], g["out_rows"]) < 2e-4
+    assert stats_close(stats(out), g["out_stats"], 1e-4)
+    if prev0 is not None:
+        assert torch.equal(prev0, inp.prev_bev)                  # the restatement does not rotate in place
+    (out * fixed_projection(out.shape)).sum().backward()
+    assert max_err(inp.bev_queries.grad[g["rows_q"]], g["grad_queries_rows"]) < 5e-4
+    for i, f in enumerate(inp.mlvl_feats):
+        assert max_err(f.grad[:, :, :8, :2], g[f"grad_feat{i}_slice"]) < 5e-4
+        assert stats_close(stats(f.grad), g[f"grad_feat{i}_stats"], 2e-3)
+    for k in ("level_embeds", "cams_embeds", "can_bus_mlp.0.weight", "can_bus_mlp.norm.bias"):
+        assert max_err(sd[k].grad, g["gfull:" + k]) < 2e-3 * max(1.0, float(np.abs(g["gfull:" + k]).max())), k
+
+
+@pytest.mark.skipif(not mmcv_stub.reference_available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("bs,with_prev", [(2, True), (1, False)])
+def test_perception_restatement_vs_reference_fp64(bs, with_prev):
+    """Against the reference's own PerceptionTransformer class (unmodified file behind the stub)."""
+    w = syn.WORKLOADS["toy"]
+    PT = mmcv_stub.load_reference_transformer()
+    m = PT(num_feature_levels=len(w.levels), num_cams=w.num_cams, encoder=syn.encoder_cfg(w), decoder=None,
+           embed_dims=w.embed_dims, rotate_center=[w.bev_h // 2, w.bev_w // 2])
+    sd = syn.make_perception_state_dict(w)
+    m.load_state_dict(sd)
+    m = m.double().eval()
+    inp = syn.make_perception_inputs(w, bs=bs, with_prev=with_prev, dtype=torch.float64)
+    prev = None if inp.prev_bev is None else inp.prev_bev.clone()
+    with torch.no_grad():
+        ref = m.get_bev_features(inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w,
+                                 grid_length=_grid_length(w), bev_pos=inp.bev_pos, prev_bev=prev,
+                                 img_metas=inp.img_metas)
+        mine = _per_restatement(w, inp, {k: v.double() for k, v in sd.items()})
+    assert max_err(mine, ref) < 1e-9

@@ -117,3 +117,29 @@ def test_no_cpu_fallback():
     inp = syn.make_encoder_inputs(w)
     with pytest.raises(RuntimeError, match="CUDA"):
         enc(inp.bev_query, inp.feat, inp.feat, **inp.kwargs())
+
+
+@pytest.mark.skipif(not mmcv_stub.reference_available(), reason="/root/reference not mounted")
+def test_perception_transformer_state_dict_matches_reference():
+    """Same parameter names and shapes as the reference PerceptionTransformer (decoder=None)."""
+    from bevformer_b200.plugin import PerceptionTransformer
+    w = syn.WORKLOADS["toy"]
+    kw = dict(num_feature_levels=len(w.levels), num_cams=w.num_cams, encoder=syn.encoder_cfg(w),
+              decoder=None, embed_dims=w.embed_dims)
+    ours = PerceptionTransformer(**kw)
+    ref = mmcv_stub.load_reference_transformer()(**kw)
+    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert a == b
+    ours.load_state_dict(ref.state_dict())
+
+
+def test_perception_transformer_has_no_cpu_path():
+    from bevformer_b200.plugin import PerceptionTransformer
+    w = syn.WORKLOADS["toy"]
+    m = PerceptionTransformer(num_feature_levels=len(w.levels), num_cams=w.num_cams,
+                              encoder=syn.encoder_cfg(w), decoder=None, embed_dims=w.embed_dims)
+    inp = syn.make_perception_inputs(w, bs=1)
+    with pytest.raises(RuntimeError):
+        m.get_bev_features(inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w, bev_pos=inp.bev_pos,
+                           prev_bev=inp.prev_bev, img_metas=inp.img_metas)

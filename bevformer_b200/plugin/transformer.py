@@ -90,13 +90,16 @@ class PerceptionTransformer(nn.Module):
 
     def _rotate_prev(self, prev_bev, img_metas, bev_h, bev_w):
         """prev_bev (Nq, bs, C) rotated by each sample's yaw delta (transformer.py:142-153).  Unlike
-        the reference, the caller's tensor is left untouched (the result is a new tensor)."""
+        the reference, the caller's tensor is left untouched (the result is a new tensor), and the
+        sampling grid is always built in fp32: torchvision builds it in the image's dtype, and a
+        bf16 / fp16 grid (8-11 mantissa bits for coordinates up to +-100) picks wrong source cells for
+        the nearest-neighbour lookup.  The values themselves are copied, so the result is exact."""
         from torchvision.transforms.functional import rotate
         out = torch.empty_like(prev_bev)
         for i in range(prev_bev.shape[1]):
             img = prev_bev[:, i].reshape(bev_h, bev_w, -1).permute(2, 0, 1)
-            img = rotate(img, img_metas[i]["can_bus"][-1], center=self.rotate_center)
-            out[:, i] = img.permute(1, 2, 0).reshape(bev_h * bev_w, -1)
+            img = rotate(img.float(), img_metas[i]["can_bus"][-1], center=self.rotate_center)
+            out[:, i] = img.permute(1, 2, 0).reshape(bev_h * bev_w, -1).to(out.dtype)
         return out
 
     def get_bev_features(self, mlvl_feats, bev_queries, bev_h, bev_w, grid_length=[0.512, 0.512],

@@ -18,8 +18,8 @@ def robust_close(got, want, tol, max_outlier_frac=0.02):
     sits on a cell boundary, so two correct implementations that differ by one ulp in a location
     disagree completely on the few samples that straddle a boundary.  Compare in relative L2 and by
     the fraction of outlying elements instead of the maximum error."""
-    got = torch.as_tensor(got).double().flatten()
-    want = torch.as_tensor(want).double().flatten()
+    got = torch.as_tensor(got).detach().double().cpu().flatten()
+    want = torch.as_tensor(want).detach().double().cpu().flatten()
     scale = max(1.0, want.abs().max().item())
     l2 = ((got - want).norm() / max(want.norm().item(), 1e-12)).item()
     frac = ((got - want).abs() > tol * scale).double().mean().item()

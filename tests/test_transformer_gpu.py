@@ -8,7 +8,7 @@ from bevformer_b200 import _lib, ops, synthetic as syn
 from bevformer_b200.plugin import PerceptionTransformer
 from oracle import torch_ref
 from tests.test_encoder_gpu import robust_close
-from tests.util import fixed_projection, golden, max_err, stats, stats_close
+from tests.util import fixed_projection, golden, max_err, rel_err, stats, stats_close
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -93,21 +93,19 @@ def test_get_bev_features_fp32_vs_golden(name, workload, bs, with_prev):
         assert ok, (k, info)
 
 
-def test_get_bev_features_bf16_close_to_restatement():
-    w, m = _build("tiny", torch.bfloat16)
-    inp = syn.make_perception_inputs(w, bs=1, device=DEV, dtype=torch.bfloat16)
+@pytest.mark.parametrize("name,workload,bs,with_prev", [("toy", "toy", 2, True), ("tiny", "tiny", 1, True)])
+def test_get_bev_features_bf16_vs_golden(name, workload, bs, with_prev):
+    """bf16 storage against the fp32 golden vectors of the reference class; same bar as the bf16
+    encoder test (six layers of bf16 GEMMs + LayerNorm sit between)."""
+    g = golden("perception_" + name)
+    w, m = _build(workload, torch.bfloat16)
+    inp = syn.make_perception_inputs(w, bs=bs, with_prev=with_prev, device=DEV, dtype=torch.bfloat16)
     with torch.no_grad():
         out = m.get_bev_features(inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w, grid_length=_grid_length(w),
                                  bev_pos=inp.bev_pos, prev_bev=inp.prev_bev, img_metas=inp.img_metas)
-    cpu = syn.make_perception_inputs(w, bs=1)
-    sd = syn.make_perception_state_dict(w)
-    with torch.no_grad():
-        ref = torch_ref.get_bev_features(sd, w.num_layers, cpu.mlvl_feats, cpu.bev_queries, w.bev_h, w.bev_w,
-                                         grid_length=_grid_length(w), bev_pos=cpu.bev_pos, prev_bev=cpu.prev_bev,
-                                         img_metas=cpu.img_metas, rotate_center=(w.bev_h // 2, w.bev_w // 2),
-                                         tsa_points=w.tsa_points, sca_points=w.sca_points)
-    err = (out.float().cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item())
-    assert err < 6e-2, err                                    # same bound as the bf16 encoder test
+    assert out.dtype == torch.bfloat16
+    assert rel_err(out.float()[:, g["rows_q"]], g["out_rows"]) < 6e-2
+    assert stats_close(stats(out.float()), g["out_stats"], 3e-2)
 
 
 def test_forward_is_out_of_scope():

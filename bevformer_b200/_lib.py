@@ -37,7 +37,8 @@ SIGNATURES = {
     "bevf_layernorm_forward": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 5
                                + [c_int64, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_uint64, c_void_p,
                                   c_int, c_void_p]),
-    "bevf_layernorm_backward": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 8
+    "bevf_layernorm_backward": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 4 + [c_int64]
+                                + [c_void_p] * 4
                                 + [c_int64, c_int, ctypes.c_float, ctypes.c_uint64, c_void_p, c_int,
                                    c_void_p]),
     "bevf_sca_combine_forward": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),

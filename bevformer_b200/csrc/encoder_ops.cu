@@ -598,7 +598,7 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
               const T *__restrict__ dy, const T *__restrict__ dy2, T *__restrict__ dx,
               T *__restrict__ dres, float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows,
               int rows_per_cta, float drop_p, unsigned long long seed,
-              const unsigned long long *__restrict__ seed_base) {
+              const unsigned long long *__restrict__ seed_base, long long ld2) {
     constexpr int PER = C / 32;
     constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
     if (seed_base) seed += *seed_base;
@@ -621,7 +621,7 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
         xr.load(x + row * C, lane);
         if (res) rr.load(res + row * C, lane);
         gr.load(dy + row * C, lane);
-        if (dy2) g2r.load(dy2 + row * C, lane);
+        if (dy2) g2r.load(dy2 + row * ld2, lane);
     }
 #pragma unroll 1
     for (; row < row_end; row += kStep) {
@@ -630,7 +630,7 @@ layernorm_bwd(const T *__restrict__ x, const T *__restrict__ res, const TP *__re
             xn.load(x + nxt * C, lane);
             if (res) rn.load(res + nxt * C, lane);
             gn.load(dy + nxt * C, lane);
-            if (dy2) g2n.load(dy2 + nxt * C, lane);
+            if (dy2) g2n.load(dy2 + nxt * ld2, lane);
         }
         const float mean = mean_in[row], rstd = rstd_in[row];
         float xh[PER], g[PER], msk[PER];
@@ -1102,16 +1102,16 @@ template <typename T, typename TP>
 static int ln_bwd_t(const char *who, const void *x, const void *res, const void *gamma, const float *mean,
                     const float *rstd, const void *dy, const void *dy2, void *dx, void *dres, float *dgamma,
                     float *dbeta, long long rows, int C, float drop_p, unsigned long long seed,
-                    const unsigned long long *sb, cudaStream_t st) {
+                    const unsigned long long *sb, long long ld2, cudaStream_t st) {
     // ~4 CTAs per SM worth of row chunks keeps the per-channel atomics few
     int rows_per_cta = (int)((rows + 148 * 4 - 1) / (148 * 4));
     rows_per_cta = ((rows_per_cta + 7) / 8) * 8;
     if (rows_per_cta < 8) rows_per_cta = 8;
     const unsigned grid = blocks_for(rows, rows_per_cta);
     if (C == 256)
-        layernorm_bwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed, sb);
+        layernorm_bwd<T, TP, 256><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed, sb, ld2);
     else if (C == 512)
-        layernorm_bwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed, sb);
+        layernorm_bwd<T, TP, 512><<<grid, kEThreads, 0, st>>>((const T *)x, (const T *)res, (const TP *)gamma, mean, rstd, (const T *)dy, (const T *)dy2, (T *)dx, (T *)dres, dgamma, dbeta, rows, rows_per_cta, drop_p, seed, sb, ld2);
     else
         return fail("%s: embed_dims must be 256 or 512", who);
     return check_launch(who);
@@ -1119,7 +1119,8 @@ static int ln_bwd_t(const char *who, const void *x, const void *res, const void 
 
 extern "C" int bevf_layernorm_backward(const void *x, const void *residual, const void *gamma,
                                        int param_dtype, const float *mean, const float *rstd,
-                                       const void *dy, const void *dy_plus_pos, void *dx, void *dres,
+                                       const void *dy, const void *dy_plus_pos, int64_t dy_plus_pos_ld, void *dx,
+                                       void *dres,
                                        float *dgamma, float *dbeta, int64_t rows, int C, float drop_p,
                                        uint64_t seed, const uint64_t *seed_base, int dtype,
                                        void *stream) {
@@ -1128,17 +1129,19 @@ extern "C" int bevf_layernorm_backward(const void *x, const void *residual, cons
     BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");
     if (rows == 0) return 0;
     BEVF_REQUIRE(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, who, "null pointer argument");
+    const long long ld2 = dy_plus_pos_ld > 0 ? (long long)dy_plus_pos_ld : (long long)C;
+    BEVF_REQUIRE(ld2 >= C && ld2 % (dtype == BEVF_DTYPE_BF16 ? 8 : 4) == 0, who, "bad row stride of dy_plus_pos");
     BEVF_REQUIRE(drop_p == 0.f || dres != nullptr || residual == nullptr, who, "dropout with a residual needs a separate dres buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const bool pb = param_dtype == BEVF_DTYPE_BF16;
     BEVF_REQUIRE(pb || param_dtype == BEVF_DTYPE_F32, who, "unsupported parameter dtype code");
     if (dtype == BEVF_DTYPE_F32) {
         if (pb) return fail("%s: bf16 parameters with fp32 activations are not supported", who);
-        return ln_bwd_t<float, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, st);
+        return ln_bwd_t<float, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, ld2, st);
     }
     if (dtype == BEVF_DTYPE_BF16) {
-        if (pb) return ln_bwd_t<bf16, bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, st);
-        return ln_bwd_t<bf16, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, st);
+        if (pb) return ln_bwd_t<bf16, bf16>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, ld2, st);
+        return ln_bwd_t<bf16, float>(who, x, residual, gamma, mean, rstd, dy, dy_plus_pos, dx, dres, dgamma, dbeta, rows, C, drop_p, seed, sb, ld2, st);
     }
     return fail("%s: unsupported dtype code", who);
 }

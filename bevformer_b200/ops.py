@@ -439,14 +439,26 @@ class LayerNormResidual(Function):
         if dy is None:                                   # only y + pos was used downstream
             dy, dy2 = dy2, None
         dy = dy.contiguous()
-        dy2 = None if dy2 is None else dy2.contiguous()
+        ld2 = 0
+        if dy2 is not None:
+            # usually a column slice of the gradient of cat([prev_bev, query + pos]): rows at a
+            # uniform stride are read in place
+            r2 = dy2.reshape(-1, C) if dy2.is_contiguous() else dy2
+            uniform = (r2.stride(-1) == 1 and r2.dim() >= 2 and r2.stride(-2) >= C
+                       and all(r2.stride(i) == r2.stride(i + 1) * r2.shape[i + 1] for i in range(r2.dim() - 2))
+                       and r2.stride(-2) % 8 == 0 and r2.data_ptr() % 16 == 0)
+            if uniform:
+                ld2 = int(r2.stride(-2))
+                dy2 = r2
+            else:
+                dy2 = dy2.contiguous()
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (has_res and drop_p > 0.0) else None
         dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(x.device):
             st = lib.bevf_layernorm_backward(x.data_ptr(), _ptr(res), g.data_ptr(), pd, mean.data_ptr(),
-                                             rstd.data_ptr(), dy.data_ptr(), _ptr(dy2), dx.data_ptr(),
+                                             rstd.data_ptr(), dy.data_ptr(), _ptr(dy2), ld2, dx.data_ptr(),
                                              _ptr(dres), dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C,
                                              drop_p, seed,
                                              _ptr(seed_state(x.device)) if drop_p > 0.0 else 0,

@@ -188,12 +188,14 @@ BEVF_API int bevf_layernorm_forward(const void *x, const void *residual, const v
 
 /* dx (rows, C) = gradient of x, fully overwritten; dres = gradient of residual (may be NULL when
  * drop_p == 0: it then equals dx); dgamma / dbeta (C,) f32 are ACCUMULATED INTO.  dy_plus_pos may be
- * NULL.  drop_p / seed must be the forward call's. */
+ * NULL; its rows may be strided (dy_plus_pos_ld elements between rows, 0 = C): it usually arrives as a
+ * column slice of the gradient of cat([prev_bev, query + pos]).  drop_p / seed must be the forward call's. */
 BEVF_API int bevf_layernorm_backward(const void *x, const void *residual, const void *gamma,
                                      int param_dtype, const float *mean, const float *rstd,
-                                     const void *dy, const void *dy_plus_pos, void *dx, void *dres,
-                                     float *dgamma, float *dbeta, int64_t rows, int C, float drop_p,
-                                     uint64_t seed, const uint64_t *seed_base, int dtype, void *stream);
+                                     const void *dy, const void *dy_plus_pos, int64_t dy_plus_pos_ld,
+                                     void *dx, void *dres, float *dgamma, float *dbeta, int64_t rows,
+                                     int C, float drop_p, uint64_t seed, const uint64_t *seed_base,
+                                     int dtype, void *stream);
 
 /*
  * slots[b,q,:] = inv_count[b,q] * sum_{cameras seeing q} out[b*R + pair_of[cam][q], :]

@@ -142,4 +142,14 @@ class PerceptionTransformer(nn.Module):
             "object-query decoder of the reference forward (transformer.py:203-289) is out of scope")
 
 
+def patch_reference(cls):
+    """Install this module's ``get_bev_features`` on the reference's own PerceptionTransformer class
+    (which keeps its decoder ``forward``): ``patch_reference(PerceptionTransformer)`` once at import
+    time of a BEVFormer checkout.  Parameter / attribute names are the reference's, so nothing else
+    changes; the encoder inside is whatever the config built (the drop-in BEVFormerEncoder)."""
+    for name in ("get_bev_features", "_shift", "_rotate_prev"):
+        setattr(cls, name, getattr(PerceptionTransformer, name))
+    return cls
+
+
 _register(TRANSFORMER, PerceptionTransformer)

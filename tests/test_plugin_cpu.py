@@ -143,3 +143,21 @@ def test_perception_transformer_has_no_cpu_path():
     with pytest.raises(RuntimeError):
         m.get_bev_features(inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w, bev_pos=inp.bev_pos,
                            prev_bev=inp.prev_bev, img_metas=inp.img_metas)
+
+
+@pytest.mark.skipif(not mmcv_stub.reference_available(), reason="/root/reference not mounted")
+def test_patch_reference_installs_get_bev_features():
+    """the reference class keeps its decoder forward and gains our get_bev_features."""
+    from bevformer_b200.plugin.transformer import PerceptionTransformer, patch_reference
+    ref_cls = mmcv_stub.load_reference_transformer()
+    sub = type("Patched", (ref_cls,), {})          # patch a subclass: the loaded reference class stays pristine
+    patch_reference(sub)
+    assert sub.get_bev_features is PerceptionTransformer.get_bev_features
+    assert sub.forward is ref_cls.forward
+    w = syn.WORKLOADS["toy"]
+    m = sub(num_feature_levels=len(w.levels), num_cams=w.num_cams, encoder=syn.encoder_cfg(w), decoder=None,
+            embed_dims=w.embed_dims)
+    inp = syn.make_perception_inputs(w, bs=1)
+    with pytest.raises(RuntimeError, match="CUDA"):     # our method runs (and refuses CPU tensors)
+        m.get_bev_features(inp.mlvl_feats, inp.bev_queries, w.bev_h, w.bev_w, bev_pos=inp.bev_pos,
+                           prev_bev=inp.prev_bev, img_metas=inp.img_metas)

@@ -9,12 +9,29 @@ import sys, numpy as np, torch
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from bevformer_b200 import synthetic as syn
-from oracle import torch_ref
 w = syn.WORKLOADS["base"]
 metas = syn.make_img_metas(w, 1)
-ref3d = torch_ref.reference_points_3d(w.bev_h, w.bev_w, syn.PC_RANGE[5]-syn.PC_RANGE[2], 4, 1, torch.float32)
-ref_cam, mask = torch_ref.point_sampling(ref3d, syn.PC_RANGE, metas)   # (cam, B, Nq, D, 2), (cam,B,Nq,D)
-ref_cam = ref_cam[:,0].numpy(); mask = mask[:,0].numpy()
+def project_pillars(w, metas):
+    """Pillar anchors of every BEV query projected into every camera (float64 numpy; this tool only needs
+    the geometry, so it does its own projection instead of borrowing the test oracle's)."""
+    pc = syn.PC_RANGE
+    xs = (np.arange(w.bev_w) + 0.5) / w.bev_w * (pc[3] - pc[0]) + pc[0]
+    ys = (np.arange(w.bev_h) + 0.5) / w.bev_h * (pc[4] - pc[1]) + pc[1]
+    zs = (np.linspace(0.5, 7.5, 4) / 8.0) * (pc[5] - pc[2]) + pc[2]
+    X, Y = np.meshgrid(xs, ys)                                  # q = i * W + j
+    pts = np.stack([np.broadcast_to(X.reshape(-1, 1), (X.size, 4)), np.broadcast_to(Y.reshape(-1, 1), (X.size, 4)),
+                    np.broadcast_to(zs[None, :], (X.size, 4)), np.ones((X.size, 4))], -1)   # (Nq, D, 4)
+    l2i = np.asarray(metas[0]["lidar2img"], dtype=np.float64)    # (cam, 4, 4)
+    cam = np.einsum("cij,qdj->cqdi", l2i, pts)
+    depth = cam[..., 2]
+    xy = cam[..., :2] / np.maximum(depth, 1e-5)[..., None]
+    h, wd = metas[0]["img_shape"][0][:2]
+    xy = xy / np.array([wd, h])
+    ok = (depth > 1e-5) & (xy[..., 0] > 0) & (xy[..., 0] < 1) & (xy[..., 1] > 0) & (xy[..., 1] < 1)
+    return xy.astype(np.float32), ok
+
+
+ref_cam, mask = project_pillars(w, metas)                       # (cam, Nq, D, 2), (cam, Nq, D)
 vis = mask.any(-1)   # (cam, Nq)
 sd = syn.make_state_dict(w)
 bias = sd["layers.0.attentions.1.deformable_attention.sampling_offsets.bias"].view(8,4,8,2).numpy()  # (M,L,P,2)

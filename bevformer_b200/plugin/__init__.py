@@ -1,5 +1,6 @@
 """Host-side mirror of the reference's plugin interface for the BEV-encoder hot path
 (projects/mmdet3d_plugin/bevformer/modules/__init__.py:3-5 exports the same names)."""
+from .decoder import CustomMSDeformableAttention
 from .encoder import FFN, BEVFormerEncoder, BEVFormerLayer, MyCustomBaseTransformerLayer
 from .registry import (ATTENTION, FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                        build_attention, build_from_cfg, build_transformer_layer,
@@ -8,7 +9,7 @@ from .spatial_cross_attention import MSDeformableAttention3D, ScaPlan, SpatialCr
 from .temporal_self_attention import TemporalSelfAttention
 from .transformer import PerceptionTransformer
 
-__all__ = ["PerceptionTransformer", "BEVFormerEncoder", "BEVFormerLayer", "MyCustomBaseTransformerLayer", "FFN",
+__all__ = ["PerceptionTransformer", "CustomMSDeformableAttention", "BEVFormerEncoder", "BEVFormerLayer", "MyCustomBaseTransformerLayer", "FFN",
            "SpatialCrossAttention", "MSDeformableAttention3D", "TemporalSelfAttention", "ScaPlan",
            "ATTENTION", "FEEDFORWARD_NETWORK", "TRANSFORMER_LAYER", "TRANSFORMER_LAYER_SEQUENCE",
            "build_attention", "build_from_cfg", "build_transformer_layer",

@@ -306,3 +306,35 @@ def get_bev_features(sd: Dict[str, Tensor], num_layers: int, mlvl_feats, bev_que
     return encoder_forward(sd, num_layers, q, feat, bev_h=bev_h, bev_w=bev_w, bev_pos=pos,
                            spatial_shapes=ss, level_start_index=lsi, prev_bev=prev_bev, shift=shift,
                            img_metas=img_metas, prefix="encoder.", **encoder_kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder cross-attention (modules/decoder.py:233-345), functional, batch-first inputs
+# ------------------------------------------------------------------------------------------------
+def custom_ms_deformable_attention(sd, pre, query: Tensor, value: Tensor, reference_points: Tensor,
+                                   spatial_shapes, sampler, query_pos: Optional[Tensor] = None,
+                                   key_padding_mask: Optional[Tensor] = None, num_heads=8,
+                                   num_points=4) -> Tensor:
+    """query (bs, Nq, C), value (bs, S, C), reference_points (bs, Nq, L, 2|4); eval mode.
+    Returns output_proj(sampled) + query (identity = the query before query_pos is added)."""
+    bs, nq, c = query.shape
+    ss = [(int(h), int(w)) for h, w in torch.as_tensor(spatial_shapes).tolist()]
+    nl = len(ss)
+    q = query if query_pos is None else query + query_pos
+    v = _lin(sd, pre + "value_proj", value)
+    if key_padding_mask is not None:
+        v = v.masked_fill(key_padding_mask[..., None], 0.0)
+    v = v.view(bs, value.shape[1], num_heads, -1)
+    off = _lin(sd, pre + "sampling_offsets", q).view(bs, nq, num_heads, nl, num_points, 2)
+    att = _lin(sd, pre + "attention_weights", q).view(bs, nq, num_heads, nl * num_points).softmax(-1)
+    att = att.view(bs, nq, num_heads, nl, num_points)
+    if reference_points.shape[-1] == 2:
+        norm = torch.tensor([[w, h] for h, w in ss], dtype=query.dtype)
+        loc = reference_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = reference_points[:, :, None, :, None, :2] + off / num_points * reference_points[:, :, None, :, None, 2:] * 0.5
+    lsi = [0]
+    for h, w in ss[:-1]:
+        lsi.append(lsi[-1] + h * w)
+    out = sampler(v, ss, lsi, loc, att)
+    return _lin(sd, pre + "output_proj", out) + query

@@ -7,9 +7,9 @@ from .registry import (ATTENTION, FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, TRANSF
                        build_transformer_layer_sequence)
 from .spatial_cross_attention import MSDeformableAttention3D, ScaPlan, SpatialCrossAttention
 from .temporal_self_attention import TemporalSelfAttention
-from .transformer import PerceptionTransformer
+from .transformer import PerceptionTransformer, PerceptionTransformerBEVEncoder
 
-__all__ = ["PerceptionTransformer", "CustomMSDeformableAttention", "BEVFormerEncoder", "BEVFormerLayer", "MyCustomBaseTransformerLayer", "FFN",
+__all__ = ["PerceptionTransformer", "PerceptionTransformerBEVEncoder", "CustomMSDeformableAttention", "BEVFormerEncoder", "BEVFormerLayer", "MyCustomBaseTransformerLayer", "FFN",
            "SpatialCrossAttention", "MSDeformableAttention3D", "TemporalSelfAttention", "ScaPlan",
            "ATTENTION", "FEEDFORWARD_NETWORK", "TRANSFORMER_LAYER", "TRANSFORMER_LAYER_SEQUENCE",
            "build_attention", "build_from_cfg", "build_transformer_layer",

@@ -142,6 +142,85 @@ class PerceptionTransformer(nn.Module):
             "object-query decoder of the reference forward (transformer.py:203-289) is out of scope")
 
 
+class PerceptionTransformerBEVEncoder(nn.Module):
+    """BEVFormerV2's wrapper around the same encoder (modules/transformerV2.py:54-174): camera / level
+    embeddings + flatten, then the encoder WITHOUT temporal input (prev_bev=None, zero shift), then --
+    only when the data pipeline applied a global BEV augmentation -- a resampling of the result onto the
+    augmented grid.  Same constructor arguments, parameter names and forward signature."""
+
+    def __init__(self, num_feature_levels=4, num_cams=6, two_stage_num_proposals=300, encoder=None,
+                 embed_dims=256, use_cams_embeds=True, rotate_center=[100, 100], init_cfg=None, **kwargs):
+        super().__init__()
+        self.init_cfg = init_cfg
+        self.encoder = build_transformer_layer_sequence(encoder)
+        self.embed_dims = embed_dims
+        self.num_feature_levels = num_feature_levels
+        self.num_cams = num_cams
+        self.fp16_enabled = False
+        self.use_cams_embeds = use_cams_embeds
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.rotate_center = rotate_center
+        self.level_embeds = nn.Parameter(torch.empty(num_feature_levels, embed_dims))
+        if use_cams_embeds:
+            self.cams_embeds = nn.Parameter(torch.empty(num_cams, embed_dims))
+        self.init_weights()
+
+    def init_weights(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if type(m).__name__ in ("MSDeformableAttention3D", "TemporalSelfAttention",
+                                    "CustomMSDeformableAttention"):
+                (getattr(m, "init_weight", None) or m.init_weights)()
+        nn.init.normal_(self.level_embeds)
+        if self.use_cams_embeds:
+            nn.init.normal_(self.cams_embeds)
+
+    def forward(self, mlvl_feats, bev_queries, bev_h, bev_w, grid_length=[0.512, 0.512], bev_pos=None,
+                prev_bev=None, **kwargs):
+        """Returns the BEV features (bs, bev_h*bev_w, C); ``prev_bev`` is accepted and ignored, as in
+        the reference (:97-141)."""
+        if not mlvl_feats[0].is_cuda:
+            raise RuntimeError("PerceptionTransformerBEVEncoder: CUDA tensors required "
+                               "(bevformer_b200 has no CPU path)")
+        bs = mlvl_feats[0].size(0)
+        bev_queries = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+        bev_pos = bev_pos.flatten(2).permute(2, 0, 1)
+        feat_flatten = ops.FlattenFeats.apply(self.cams_embeds if self.use_cams_embeds else None,
+                                              self.level_embeds, *mlvl_feats)
+        spatial_shapes = torch.as_tensor([tuple(f.shape[-2:]) for f in mlvl_feats], dtype=torch.long,
+                                         device=bev_pos.device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)),
+                                       spatial_shapes.prod(1).cumsum(0)[:-1]))
+        bev_embed = self.encoder(bev_queries, feat_flatten, feat_flatten, bev_h=bev_h, bev_w=bev_w,
+                                 bev_pos=bev_pos, spatial_shapes=spatial_shapes,
+                                 level_start_index=level_start_index, prev_bev=None,
+                                 shift=bev_queries.new_tensor([0, 0]).unsqueeze(0), **kwargs)
+        return self._align_to_augmentation(bev_embed, kwargs["img_metas"], bs, bev_h, bev_w)
+
+    @staticmethod
+    def _align_to_augmentation(bev, img_metas, bs, bev_h, bev_w):
+        """transformerV2.py:142-174: with a GlobalRotScaleTransImage augmentation that only moved the
+        ground truth, the BEV map is resampled through the 2x2 part of the augmentation matrix (bilinear
+        grid_sample); with the augmentation applied to the images too it is only re-laid-out; without it
+        the encoder output is returned as is.  Once per training sample, tensor ops as in the reference."""
+        aug = img_metas[0].get("aug_param", {}) if isinstance(img_metas[0], dict) else {}
+        if "GlobalRotScaleTransImage_param" not in aug:
+            return bev
+        _rot, _scale, _fx, _fy, bda_mat, only_gt = aug["GlobalRotScaleTransImage_param"]
+        img = bev.reshape(bs, bev_h, bev_w, -1).permute(0, 3, 1, 2)
+        if only_gt:
+            ys = torch.linspace(0.5, bev_h - 0.5, bev_h, dtype=bev.dtype, device=bev.device) / bev_h
+            xs = torch.linspace(0.5, bev_w - 0.5, bev_w, dtype=bev.dtype, device=bev.device) / bev_w
+            ref_y, ref_x = torch.meshgrid(ys, xs, indexing="ij")
+            grid = (torch.stack((ref_x, ref_y), -1) * 2.0 - 1.0).unsqueeze(0).unsqueeze(-1)
+            mat = torch.as_tensor(bda_mat)[:2, :2].to(grid).view(1, 1, 1, 2, 2)
+            grid = torch.matmul(mat, grid).squeeze(-1)
+            img = torch.nn.functional.grid_sample(img, grid.expand(bs, -1, -1, -1), align_corners=False)
+        return img.reshape(bs, -1, bev_h * bev_w).permute(0, 2, 1)
+
+
 def patch_reference(cls):
     """Install this module's ``get_bev_features`` on the reference's own PerceptionTransformer class
     (which keeps its decoder ``forward``): ``patch_reference(PerceptionTransformer)`` once at import
@@ -153,3 +232,4 @@ def patch_reference(cls):
 
 
 _register(TRANSFORMER, PerceptionTransformer)
+_register(TRANSFORMER, PerceptionTransformerBEVEncoder)

@@ -338,3 +338,35 @@ def custom_ms_deformable_attention(sd, pre, query: Tensor, value: Tensor, refere
         lsi.append(lsi[-1] + h * w)
     out = sampler(v, ss, lsi, loc, att)
     return _lin(sd, pre + "output_proj", out) + query
+
+
+# ------------------------------------------------------------------------------------------------
+# BEVFormerV2: PerceptionTransformerBEVEncoder.forward (modules/transformerV2.py:97-174)
+# ------------------------------------------------------------------------------------------------
+def bev_encoder_v2(sd: Dict[str, Tensor], num_layers: int, mlvl_feats, bev_queries: Tensor, bev_h: int,
+                   bev_w: int, *, bev_pos: Tensor, img_metas, use_cams_embeds=True, **encoder_kwargs) -> Tensor:
+    """Embeddings + flatten, encoder without temporal input (prev_bev=None, zero shift), then the
+    optional resampling onto the augmented BEV grid.  Returns (bs, Nq, C)."""
+    bs = mlvl_feats[0].shape[0]
+    q = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+    pos = bev_pos.flatten(2).permute(2, 0, 1)
+    feat, ss, lsi = flatten_feats(mlvl_feats, sd["cams_embeds"] if use_cams_embeds else None,
+                                  sd["level_embeds"])
+    bev = encoder_forward(sd, num_layers, q, feat, bev_h=bev_h, bev_w=bev_w, bev_pos=pos,
+                          spatial_shapes=ss, level_start_index=lsi, prev_bev=None,
+                          shift=q.new_tensor([0, 0]).unsqueeze(0), img_metas=img_metas,
+                          prefix="encoder.", **encoder_kwargs)
+    aug = img_metas[0].get("aug_param", {})
+    if "GlobalRotScaleTransImage_param" not in aug:
+        return bev
+    _rot, _scale, _fx, _fy, bda_mat, only_gt = aug["GlobalRotScaleTransImage_param"]
+    img = bev.reshape(bs, bev_h, bev_w, -1).permute(0, 3, 1, 2)
+    if only_gt:
+        ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, bev_h - 0.5, bev_h, dtype=q.dtype),
+                                      torch.linspace(0.5, bev_w - 0.5, bev_w, dtype=q.dtype), indexing="ij")
+        grid = torch.stack((ref_x / bev_w, ref_y / bev_h), -1) * 2.0 - 1.0
+        grid = grid.unsqueeze(0).unsqueeze(-1)
+        mat = torch.as_tensor(bda_mat)[:2, :2].to(grid).view(1, 1, 1, 2, 2)
+        grid = torch.matmul(mat, grid).squeeze(-1)
+        img = F.grid_sample(img, grid.expand(bs, -1, -1, -1), align_corners=False)
+    return img.reshape(bs, -1, bev_h * bev_w).permute(0, 2, 1)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# final round check: full GPU test suite, smoke(), default bench (with cpu_baseline), reference arm
+# round-end check: full GPU test suite, smoke(), default bench (with cpu_baseline), reference arm
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2

@@ -44,7 +44,8 @@ def _sampler(use_c_oracle: bool):
     if not use_c_oracle:
         return lambda v, ss, lsi, loc, a: msda_grid_sample(v, ss, loc, a)
     from .msda_oracle import MSDAOracleFunction
-    return lambda v, ss, lsi, loc, a: MSDAOracleFunction.apply(v, ss, lsi, loc, a, 64)
+    return lambda v, ss, lsi, loc, a: MSDAOracleFunction.apply(
+        v, torch.as_tensor(ss, dtype=torch.int64), torch.as_tensor(lsi, dtype=torch.int64), loc, a, 64)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -135,7 +135,9 @@ def test_dropin_on_gpu_vs_restatement(levels, points, nq, bs, ref_dim, with_mask
     m.load_state_dict(sd)
     m = m.to("cuda", dtype).eval()
     dev = {k: (v.cuda() if v is not None else None) for k, v in case.items()}
-    for k in ("query", "query_pos", "value", "reference_points"):
+    # reference points stay fp32: a bf16 coordinate has 8 mantissa bits (0.2 px on a 50-px map), which
+    # alone moves the result by 8e-2 on the 900-query case -- an input-precision effect, not a kernel one
+    for k in ("query", "query_pos", "value"):
         dev[k] = dev[k].to(dtype)
     before = _lib.launch_count()
     with torch.no_grad():

@@ -224,3 +224,41 @@ def test_perception_restatement_vs_reference_fp64(bs, with_prev):
                                  img_metas=inp.img_metas)
         mine = _per_restatement(w, inp, {k: v.double() for k, v in sd.items()})
     assert max_err(mine, ref) < 1e-9
+
+
+# ---- randomized properties of the op, on Oracle-S -------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def _op_shapes(draw):
+    levels = draw(st.lists(st.tuples(st.integers(1, 6), st.integers(1, 7)), min_size=1, max_size=3))
+    return dict(bs=draw(st.integers(1, 2)), levels=levels, nq=draw(st.integers(1, 6)),
+                heads=draw(st.integers(1, 3)), dim=draw(st.sampled_from([1, 4, 7, 32])),
+                pts=draw(st.integers(1, 3)), seed=draw(st.integers(0, 10_000)))
+
+
+@settings(max_examples=40, deadline=None)
+@given(_op_shapes())
+def test_oracle_s_random_properties(sh):
+    v, ss, lsi, loc, attn = syn.make_msda_inputs(sh["bs"], sh["levels"], sh["nq"], sh["heads"], sh["dim"],
+                                                 sh["pts"], seed=sh["seed"], dtype=torch.float64,
+                                                 loc_range=(-0.6, 1.6))
+    out = msda_oracle.msda_forward(v, ss, lsi, loc, attn)
+    # equals the grid_sample formulation the reference falls back to (mmcv's pure-PyTorch path)
+    want = torch_ref.msda_grid_sample(v, [tuple(x) for x in ss.tolist()], loc, attn)
+    assert max_err(out, want) < 1e-12
+    # permuting the queries permutes the output rows
+    perm = torch.randperm(sh["nq"], generator=torch.Generator().manual_seed(sh["seed"]))
+    assert max_err(msda_oracle.msda_forward(v, ss, lsi, loc[:, perm], attn[:, perm]), out[:, perm]) == 0.0
+    # linear in value and in the attention weights
+    assert max_err(msda_oracle.msda_forward(2.5 * v, ss, lsi, loc, attn), 2.5 * out) < 1e-12
+    assert max_err(msda_oracle.msda_forward(v, ss, lsi, loc, 0.5 * attn), 0.5 * out) < 1e-12
+    # samples a full pixel outside the map contribute nothing: pushing every location there zeroes the output
+    assert msda_oracle.msda_forward(v, ss, lsi, loc * 0 + 7.0, attn).abs().max().item() == 0.0
+    # backward is the exact transpose: <grad_out, J dv> == <J^T grad_out, dv>
+    g = torch.randn(out.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(1 + sh["seed"]))
+    gv, _, _ = msda_oracle.msda_backward(v, ss, lsi, loc, attn, g)
+    dv = torch.randn(v.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(2 + sh["seed"]))
+    lhs = (g * msda_oracle.msda_forward(dv, ss, lsi, loc, attn)).sum()
+    assert abs(lhs.item() - (gv * dv).sum().item()) < 1e-9 * max(1.0, abs(lhs.item()))

@@ -21,7 +21,6 @@ from typing import Optional
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 from .linear import linear, linear_relu_dropout

@@ -1,6 +1,5 @@
 """GPU parity of PerceptionTransformer.get_bev_features (the encoder's caller) and of its
 feature-flattening kernel, against the golden vectors made from the reference's own class."""
-import numpy as np
 import pytest
 import torch
 

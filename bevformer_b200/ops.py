@@ -251,6 +251,8 @@ class SamplerRows(Function):
 
     @staticmethod
     def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index):
+        if value.dtype == torch.float16:      # the reference widens half inputs (…function.py:93)
+            value = value.float()
         out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         return out
@@ -358,19 +360,31 @@ def _ptr(t):
 
 _seed_counter = [0]
 _seed_state: dict = {}        # device -> int64[1] step counter living on the device
+_seed_snap: dict = {}         # device -> int64[1] copy of the counter taken by the last advance_seed()
 
 
 def seed_state(device) -> torch.Tensor:
+    """The dropout step key the kernels of the CURRENT forward read: the snapshot taken by the last
+    ``advance_seed`` (the persistent counter itself before the first one).  Autograd nodes keep the
+    tensor they were given, so a backward always regenerates the masks of its own forward even when
+    other training-mode forwards ran in between."""
     key = torch.device(device)
+    if key in _seed_snap:
+        return _seed_snap[key]
     if key not in _seed_state:
         _seed_state[key] = torch.zeros(1, dtype=torch.int64, device=key)
     return _seed_state[key]
 
 
 def advance_seed(device) -> None:
-    """Bump the device-side dropout step counter (one tiny kernel; capturable in a CUDA graph, so
-    every replay of a captured training step draws new masks)."""
-    seed_state(device).add_(0x9E3779B97F4A7C1)
+    """Bump the device-side dropout step counter and snapshot it (two tiny kernels; capturable in a
+    CUDA graph: the in-place add lives on a persistent tensor, so every replay of a captured training
+    step draws new masks, and the snapshot is recomputed by the replay)."""
+    key = torch.device(device)
+    if key not in _seed_state:
+        _seed_state[key] = torch.zeros(1, dtype=torch.int64, device=key)
+    _seed_state[key].add_(0x9E3779B97F4A7C1)
+    _seed_snap[key] = _seed_state[key].clone()
 
 
 def _next_seed() -> int:
@@ -426,6 +440,8 @@ class LayerNormResidual(Function):
                                             _ptr(sbase), _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         ctx.save_for_backward(x, rc, g, mean, rstd)
+        ctx.sbase = sbase                 # the step key of THIS forward (see seed_state)
+        ctx.pos_shape = None if pos is None else tuple(pos.shape)
         ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed, pos is not None)
         return y if pos is None else (y, y2)
 
@@ -436,6 +452,10 @@ class LayerNormResidual(Function):
         has_res, gdt, bdt, pd, drop_p, seed, has_pos = ctx.meta
         C = x.shape[-1]
         rows = x.numel() // C
+        # d(y + pos)/d pos = 1: pos (the learned BEV positional encoding) receives the gradient of y2
+        d_pos = None
+        if has_pos and ctx.needs_input_grad[6] and dy2 is not None:
+            d_pos = dy2.reshape(ctx.pos_shape)
         if dy is None:                                   # only y + pos was used downstream
             dy, dy2 = dy2, None
         dy = dy.contiguous()
@@ -461,11 +481,11 @@ class LayerNormResidual(Function):
                                              rstd.data_ptr(), dy.data_ptr(), _ptr(dy2), ld2, dx.data_ptr(),
                                              _ptr(dres), dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C,
                                              drop_p, seed,
-                                             _ptr(seed_state(x.device)) if drop_p > 0.0 else 0,
+                                             _ptr(ctx.sbase) if drop_p > 0.0 else 0,
                                              _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         d_res = None if not has_res else (dres if dres is not None else dx)
-        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None, None
+        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None, d_pos
 
 
 class ScaCombine(Function):
@@ -684,6 +704,7 @@ class FlattenFeats(Function):
                 start += hws[lvl]
         ctx.shapes = [tuple(f.shape) for f in feats]
         ctx.meta = (None if cams_embeds is None else cams_embeds.dtype, level_embeds.dtype)
+        ctx.level_shape = tuple(level_embeds.shape)       # may hold more rows than there are levels
         return out
 
     @staticmethod
@@ -693,12 +714,16 @@ class FlattenFeats(Function):
         cdt, ldt = ctx.meta
         need = ctx.needs_input_grad
         d_cams = dy.sum((1, 2), dtype=torch.float32).to(cdt) if (cdt is not None and need[0]) else None
-        d_lvl, d_feats, start = [], [], 0
+        # the reference slices level_embeds[lvl:lvl+1] (transformer.py:172): rows beyond the pyramid's
+        # levels (tiny / small: 1 level, num_feature_levels = 4) simply get a zero gradient
+        d_level = torch.zeros(ctx.level_shape, device=dy.device, dtype=torch.float32) if need[1] else None
+        d_feats, start = [], 0
         for i, (bs, ncam, C, h, w) in enumerate(ctx.shapes):
             sl = dy[:, start:start + h * w]                          # (ncam, hw, bs, C)
             if need[1]:
-                d_lvl.append(sl.sum((0, 1, 2), dtype=torch.float32))
+                d_level[i] = sl.sum((0, 1, 2), dtype=torch.float32)
             d_feats.append(sl.permute(2, 0, 3, 1).reshape(bs, ncam, C, h, w) if need[2 + i] else None)
             start += h * w
-        d_level = torch.stack(d_lvl).to(ldt) if need[1] else None
+        if need[1]:
+            d_level = d_level.to(ldt)
         return (d_cams, d_level, *d_feats)

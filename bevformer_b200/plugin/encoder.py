@@ -24,12 +24,39 @@ import torch.nn as nn
 
 from .. import ops
 from .linear import linear, linear_relu_dropout
-from .registry import (FEEDFORWARD_NETWORK, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, _register,
+from .registry import (FEEDFORWARD_NETWORK, HAVE_MMCV, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, _register,
                        build_attention, build_feedforward_network, build_transformer_layer)
 from .spatial_cross_attention import ScaPlan, SpatialCrossAttention
 from .temporal_self_attention import TemporalSelfAttention
 
 _OPS = ("self_attn", "norm", "ffn", "cross_attn")
+
+
+class _DropPath(nn.Module):
+    """mmcv's DropPath (stochastic depth per sample), for FFN(dropout_layer=dict(type='DropPath'))."""
+
+    def __init__(self, drop_prob=0.1):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x / keep * mask
+
+
+def _build_dropout(cfg):
+    if not cfg:
+        return nn.Identity()
+    cfg = dict(cfg)
+    typ = cfg.pop("type", "Dropout")
+    if typ == "Dropout":
+        return nn.Dropout(cfg.get("drop_prob", cfg.get("p", 0.5)), inplace=cfg.get("inplace", False))
+    if typ == "DropPath":
+        return _DropPath(cfg.get("drop_prob", 0.1))
+    raise KeyError(f"unsupported dropout_layer type {typ}")
 
 
 class FFN(nn.Module):
@@ -56,7 +83,7 @@ class FFN(nn.Module):
             width = feedforward_channels
         blocks += [nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop)]
         self.layers = nn.Sequential(*blocks)
-        self.dropout_layer = nn.Identity()
+        self.dropout_layer = _build_dropout(dropout_layer)      # mmcv: build_dropout(cfg) or Identity
         self.add_identity = add_identity
 
     def transform(self, x):
@@ -78,13 +105,23 @@ class FFN(nn.Module):
         return (x if identity is None else identity) + self.dropout_layer(out)
 
 
-_register(FEEDFORWARD_NETWORK, FFN, name="FFN")
+if not HAVE_MMCV:
+    # local registry only: in a real mmcv checkout 'FFN' stays mmcv's own class (the detection decoder
+    # builds its FFNs from the same registry); BEVFormer layers build THIS class directly, see
+    # MyCustomBaseTransformerLayer.__init__
+    _register(FEEDFORWARD_NETWORK, FFN, name="FFN")
 
 
 def _fused_norm(norm: nn.LayerNorm, x, residual, dropout: Optional[nn.Dropout] = None, pos=None):
     """LayerNorm(dropout(x) + residual) in one kernel (fp32 statistics; the dropout of the block
     that produced x is applied inside, active only in training mode).  With ``pos`` the kernel also
-    emits y + pos and the call returns (y, y + pos)."""
+    emits y + pos and the call returns (y, y + pos).  Shapes / dtypes the kernel does not cover
+    (fp16 activations under the reference's fp16 configs, embed_dims other than 256 / 512) take the
+    unfused CUDA ops instead."""
+    if x.dtype not in (torch.float32, torch.bfloat16) or x.shape[-1] not in (256, 512):
+        h = x if dropout is None else dropout(x)
+        y = norm(h if residual is None else h + residual)
+        return y if pos is None else (y, y + pos)
     p = dropout.p if (dropout is not None and dropout.training) else 0.0
     return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps, p, pos)
 
@@ -142,7 +179,11 @@ class MyCustomBaseTransformerLayer(nn.Module):
             cfg = dict(cfg)
             cfg.setdefault("embed_dims", self.embed_dims)
             assert cfg["embed_dims"] == self.embed_dims
-            self.ffns.append(build_feedforward_network(cfg))
+            if cfg.get("type", "FFN") == "FFN":       # the kernels' FFN, whatever mmcv registered as 'FFN'
+                cfg.pop("type", None)
+                self.ffns.append(FFN(**cfg))
+            else:
+                self.ffns.append(build_feedforward_network(cfg))
 
         if (norm_cfg or {}).get("type", "LN") != "LN":
             raise KeyError("only LayerNorm ('LN') is supported")
@@ -260,7 +301,8 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                 identity = query
             elif op == "ffn":
                 ffn = self.ffns[fi]
-                if fuse and isinstance(ffn, FFN) and ffn.add_identity:
+                if (fuse and isinstance(ffn, FFN) and ffn.add_identity
+                        and isinstance(ffn.dropout_layer, nn.Identity)):
                     emit = (carry is not None and carry.get("emit") and i + 2 == len(order)
                             and bev_pos is not None and bev_pos.dtype == query.dtype)
                     out = _fused_norm(self.norms[ni], ffn.transform(query), query,

@@ -88,6 +88,7 @@ def encoder_case(name, workload, bs=1, with_prev=True, seed=0, keep_rows=512, ba
     if backward:
         inp.bev_query.requires_grad_(True)
         inp.feat.requires_grad_(True)
+        inp.bev_pos.requires_grad_(True)      # the learned positional encoding trains (every layer's TSA adds it)
     with torch.set_grad_enabled(backward):
         out = enc(inp.bev_query, inp.feat, inp.feat, **inp.kwargs())
     rq = row_subset(w.num_query, keep_rows)
@@ -102,7 +103,9 @@ def encoder_case(name, workload, bs=1, with_prev=True, seed=0, keep_rows=512, ba
                     grad_query_rows=inp.bev_query.grad[rq].numpy(),
                     grad_query_stats=stats(inp.bev_query.grad),
                     grad_feat_rows=inp.feat.grad[:, rs].numpy(),
-                    grad_feat_stats=stats(inp.feat.grad))
+                    grad_feat_stats=stats(inp.feat.grad),
+                    grad_pos_rows=inp.bev_pos.grad[rq].numpy(),
+                    grad_pos_stats=stats(inp.bev_pos.grad))
         for k, p in enc.named_parameters():
             save["gstat:" + k] = stats(p.grad)
             if p.grad.numel() <= 1024:

@@ -84,11 +84,17 @@ def test_backward_against_golden_fp32(name, workload, bs, with_prev):
     inp = _inputs(w, bs, with_prev, torch.float32)
     inp.bev_query.requires_grad_(True)
     inp.feat.requires_grad_(True)
+    inp.bev_pos.requires_grad_(True)      # trains in the real model (LearnedPositionalEncoding)
     out = enc(inp.bev_query, inp.feat, inp.feat, **inp.kwargs())
     (out * fixed_projection(out.shape).to(DEV)).sum().backward()
     torch.cuda.synchronize()
     ok, m = robust_close(inp.bev_query.grad.cpu()[g["rows_q"]], g["grad_query_rows"], 2e-3)
     assert ok, ("grad_query", m)
+    # every layer's temporal self-attention adds bev_pos to its query: all of them feed this gradient
+    ok, m = robust_close(inp.bev_pos.grad.cpu()[g["rows_q"]], g["grad_pos_rows"], 2e-3)
+    assert ok, ("grad_pos", m)
+    got, want = stats(inp.bev_pos.grad), g["grad_pos_stats"]
+    assert np.all(np.abs(got[1:3] - want[1:3]) <= 5e-3 * np.abs(want[1:3])), ("grad_pos", got, want)
     ok, m = robust_close(inp.feat.grad.cpu()[:, g["rows_s"]], g["grad_feat_rows"], 2e-3)
     assert ok, ("grad_feat", m)
     # whole-tensor energy (sum |x|, sum x^2); max|x| is left out: one straddling sample can move it
@@ -109,24 +115,47 @@ def test_backward_against_golden_fp32(name, workload, bs, with_prev):
             assert ok, (k, m)
 
 
-@pytest.mark.parametrize("name,workload", [("toy", "toy"), ("tiny", "tiny"), ("small4", "small4")])
+def _cos(a, b):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    return torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+
+
+@pytest.mark.parametrize("name,workload", [("toy", "toy"), ("tiny", "tiny"), ("small4", "small4"),
+                                           ("base", "base")])
 def test_backward_bf16_tracks_fp32_reference(name, workload):
+    """bf16 storage (the headline configuration: base, bf16, fwd+bwd) against the fp32 golden gradients
+    of the reference's own modules: rows of d bev_query / d feat / d bev_pos and every parameter's
+    gradient.  bf16 GEMMs (rel. 2^-9 per product sum) sit between the sampler calls, so the bars are
+    direction (cosine), energy and relative L2 of the sampled rows rather than the op-level 1e-2."""
     g = golden("encoder_" + name)
     w, enc = _build(workload, torch.bfloat16)
     inp = _inputs(w, 1, True, torch.bfloat16)
     inp.bev_query.requires_grad_(True)
     inp.feat.requires_grad_(True)
+    inp.bev_pos.requires_grad_(True)
     out = enc(inp.bev_query, inp.feat, inp.feat, **inp.kwargs())
     (out.float() * fixed_projection(out.shape).to(DEV)).sum().backward()
     torch.cuda.synchronize()
-    # direction and size of the big gradients agree with the fp32 reference
-    gq = inp.bev_query.grad.float().cpu()[g["rows_q"]].flatten()
-    want = torch.from_numpy(g["grad_query_rows"]).flatten()
-    cos = torch.nn.functional.cosine_similarity(gq, want, dim=0).item()
-    assert cos > 0.98, cos
+    report = {}
+    for key, got, want in (("grad_query", inp.bev_query.grad.float().cpu()[g["rows_q"]], g["grad_query_rows"]),
+                           ("grad_feat", inp.feat.grad.float().cpu()[:, g["rows_s"]], g["grad_feat_rows"]),
+                           ("grad_pos", inp.bev_pos.grad.float().cpu()[g["rows_q"]], g["grad_pos_rows"])):
+        want = torch.from_numpy(want)
+        l2 = ((got - want).norm() / want.norm()).item()
+        report[key] = (round(_cos(got, want), 5), round(l2, 4))
+    print(name, report)
+    for key, (cos, l2) in report.items():
+        assert cos > 0.98 and l2 < 0.2, (key, cos, l2)
+    worst = (None, 0.0)
     for k, p in enc.named_parameters():
         got, ref = stats(p.grad.float()), g["gstat:" + k]
-        assert abs(got[2] - ref[2]) <= 0.15 * max(ref[2], 1e-12), (k, got, ref)   # sum of squares
+        dev = abs(got[2] - ref[2]) / max(ref[2], 1e-12)
+        worst = max(worst, (k, dev), key=lambda t: t[1])
+        assert dev <= 0.15, (k, got, ref)                                   # sum of squares
+        if "gfull:" + k in g.files:                                         # small tensors: element-wise direction
+            assert _cos(p.grad.float().cpu(), g["gfull:" + k]) > 0.97, k
+    print(name, "worst parameter-gradient energy deviation", worst)
 
 
 def test_restatement_agrees_on_fresh_seed():

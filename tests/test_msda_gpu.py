@@ -149,3 +149,62 @@ def test_base_shapes_properties(which):
     rgv, rgl, rga = msda_oracle.msda_backward(v, ss, lsi, loc, attn, torch.ones(bs, nq, 256))
     assert rel_err(gv.cpu(), rgv) < 1e-3
     assert rel_err(ga.cpu(), rga) < 1e-3 and rel_err(gl.cpu(), rgl) < 1e-3
+
+
+@pytest.mark.parametrize("which", ["sca", "tsa"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_base_rig_geometry_against_oracle(which, dtype):
+    """The launches the headline benchmark times: base shapes on the REAL geometry (SCA: the 44 511
+    in-view (camera, query) pairs of the synthetic rig, 4 levels, 8 points, through the row-list entry
+    points; TSA: 2 x 40 000 rows around each query's own cell), forward and backward, fp32 and bf16
+    storage, every output element against Oracle-S on the same (storage-rounded) inputs.
+    Bars: 1e-3 fp32 / 1e-2 bf16 (BASELINE.json north_star)."""
+    from tools.bench_msda import rig_sca_inputs, rig_tsa_inputs
+    tol = TOL[dtype]
+    if which == "sca":
+        v, ss, lsi, loc, attn, row_map = rig_sca_inputs(DEV)
+    else:
+        v, ss, lsi, loc, attn = rig_tsa_inputs(DEV)
+        row_map = None
+    vd = v.to(dtype)
+    nrows = loc.shape[0] if row_map is not None else loc.shape[0] * loc.shape[1]
+    gout = fixed_projection((nrows, 256)).to(DEV, dtype)
+    if row_map is not None:
+        out = ops.msda_rows_forward(vd, ss, lsi, loc, attn, row_map)
+        gv, gl, ga = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout)
+    else:
+        out = ops.msda_forward(vd, ss, lsi, loc, attn)
+        gv, gl, ga = ops.msda_backward(vd, ss, lsi, loc, attn, gout.view(out.shape))
+    torch.cuda.synchronize()
+    out, gv, gl, ga = out.float().cpu(), gv.cpu(), gl.cpu(), ga.cpu()
+    vr, gr = vd.float().cpu(), gout.float().cpu()
+    loc_c, attn_c = loc.cpu(), attn.cpu()
+    if row_map is not None:       # the oracle is dense: one call per camera map over that camera's rows
+        rm = row_map.cpu().long()
+        ref = torch.empty_like(out); rgv = torch.zeros_like(gv)
+        rgl = torch.empty_like(gl); rga = torch.empty_like(ga)
+        for cam in range(vr.shape[0]):
+            idx = (rm == cam).nonzero().flatten()
+            lc, ac = loc_c[idx][None].contiguous(), attn_c[idx][None].contiguous()
+            ref[idx] = msda_oracle.msda_forward(vr[cam:cam + 1], ss.cpu(), lsi.cpu(), lc, ac)[0]
+            a, b, c = msda_oracle.msda_backward(vr[cam:cam + 1], ss.cpu(), lsi.cpu(), lc, ac, gr[idx][None].contiguous())
+            rgv[cam] = a[0]; rgl[idx] = b[0]; rga[idx] = c[0]
+    else:
+        ref = msda_oracle.msda_forward(vr, ss.cpu(), lsi.cpu(), loc_c, attn_c)
+        rgv, rgl, rga = msda_oracle.msda_backward(vr, ss.cpu(), lsi.cpu(), loc_c, attn_c, gr.view(ref.shape))
+    errs = dict(out=rel_err(out.view(ref.shape), ref), grad_value=rel_err(gv, rgv),
+                grad_attn=rel_err(ga, rga), grad_loc=rel_err(gl, rgl))
+    print(which, dtype, errs)
+    assert errs["out"] < tol and errs["grad_value"] < tol and errs["grad_attn"] < tol, errs
+    # grad_loc carries the W_l / H_l factors (up to 200) and is discontinuous at cell borders: a sample
+    # whose coordinate rounds onto a border may take the other cell's slope -> compare the bulk
+    ok, m = _robust(gl, rgl, 4 * tol)
+    assert ok, ("grad_loc", m, errs)
+
+
+def _robust(got, want, tol, max_outlier_frac=1e-4):
+    got, want = got.double().flatten(), want.double().flatten()
+    scale = max(1.0, want.abs().max().item())
+    frac = ((got - want).abs() > tol * scale).double().mean().item()
+    l2 = ((got - want).norm() / max(want.norm().item(), 1e-12)).item()
+    return frac <= max_outlier_frac and l2 < 5 * tol, (l2, frac)

@@ -20,15 +20,18 @@ def _flatten_ref(feats, cams, lvl):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("use_cams", [True, False])
-def test_flatten_feats_kernel_exact(dtype, use_cams):
+@pytest.mark.parametrize("extra_level_rows", [0, 3])
+def test_flatten_feats_kernel_exact(dtype, use_cams, extra_level_rows):
     """Same arithmetic as the reference's tensor ops (cast the embedding, add, round): bit-exact,
-    including ragged tiles (hw and C not multiples of 32) and bs > 1."""
+    including ragged tiles (hw and C not multiples of 32) and bs > 1.  ``extra_level_rows``: the
+    shipped tiny / small configs feed ONE pyramid level but keep num_feature_levels = 4, so
+    level_embeds has rows no level uses -- their gradient is zero (transformer.py:172)."""
     g = torch.Generator().manual_seed(3)
     bs, ncam, C = 2, 3, 72
     shapes = [(7, 9), (4, 5), (1, 3)]
     feats = [torch.randn(bs, ncam, C, h, w, generator=g).to(DEV, dtype).requires_grad_(True) for h, w in shapes]
     cams = torch.randn(ncam, C, generator=g).to(DEV).requires_grad_(True)
-    lvl = torch.randn(len(shapes), C, generator=g).to(DEV).requires_grad_(True)
+    lvl = torch.randn(len(shapes) + extra_level_rows, C, generator=g).to(DEV).requires_grad_(True)
     before = _lib.launch_count()
     out = ops.FlattenFeats.apply(cams if use_cams else None, lvl, *feats)
     assert _lib.launch_count() - before == len(shapes)
@@ -43,6 +46,7 @@ def test_flatten_feats_kernel_exact(dtype, use_cams):
     for a, b in zip(feats, f2):
         assert torch.equal(a.grad, b.grad)
     tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert lvl.grad.shape == lvl.shape and not lvl.grad[len(shapes):].any()
     assert max_err(lvl.grad, l2.grad) <= tol * max(1.0, l2.grad.abs().max().item())
     if use_cams:
         assert max_err(cams.grad, c2.grad) <= tol * max(1.0, c2.grad.abs().max().item())

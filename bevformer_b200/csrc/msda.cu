@@ -32,6 +32,7 @@ constexpr int kMaxLevels = 16;
 constexpr int kThreads = 256;
 
 struct Corner {
+    int x0, y0;                       // top-left cell, unclamped: x0 in [-1, W-1], y0 in [-1, H-1]
     int pidx;                         // pixel index y0c*W + x0c of the (clamped) top-left corner
     int dx, dy;                       // 1 if the right / bottom neighbour is a distinct in-map pixel
     float w00, w01, w10, w11;         // bilinear weights (zero for corners outside the map / skipped)
@@ -63,6 +64,7 @@ __device__ __forceinline__ Corner make_corner(float locx, float locy, int H, int
     c.w11 = c.f11 * c.ly * c.lx;
     // Clamp into the map.  When x0 == -1 the only in-map column is x1 == 0: corner "00" then aliases
     // pixel 0 with weight 0 and corner "01" must also address pixel 0, hence dx = 0 (same for y).
+    c.x0 = x0; c.y0 = y0;
     c.pidx = max(y0, 0) * W + max(x0, 0);
     c.dx = (x0ok && x1ok) ? 1 : 0;
     c.dy = (y0ok && y1ok) ? 1 : 0;
@@ -265,7 +267,9 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
 // ------------------------------------------------------------------------------------------------
 // backward, head_dim == 32
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename TG>
+// kScatter = false: the "gather" half only (grad_loc, grad_attn); grad_value then comes from
+// msda_bwd_splat_d32 (msda_splat.cuh), which merges the reductions of neighbouring rows in registers.
+template <typename T, typename TG, bool kScatter>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const int64_t *__restrict__ level_start, const float *__restrict__ loc,
@@ -306,7 +310,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     // lanes write [16 + 4 sub, +4) -- and instruction B does the same for the high rows.  Each lane
     // therefore keeps 4 grad_out channels of its own row and 4 of its partner's, and reads the
     // partner's per-sample scalars with one extra shuffle each.
-    constexpr bool kPaired = (VEC == 8);
+    constexpr bool kPaired = (VEC == 8) && kScatter;
     const bool hi = kPaired && (grp & 4);
     const long long vrow = voff - sub * VEC;                       // element offset of the row in its map
     long long vrow_a = vrow, vrow_b = vrow;
@@ -314,6 +318,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     if constexpr (!kPaired) {
         gra[0] = g[0]; gra[1] = g[1]; gra[2] = g[2]; gra[3] = g[3];
         grb[0] = grb[1] = grb[2] = grb[3] = 0.f;
+        (void)vrow_a; (void)vrow_b;
     } else {
         const long long row_p = __shfl_xor_sync(0xffffffffu, row, 16);
         const long long vrow_p = __shfl_xor_sync(0xffffffffu, vrow, 16);
@@ -329,6 +334,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
         // ---- produce
         const int sm = s0 + sub;
         Corner c;
+        c.x0 = c.y0 = 0;
         c.pidx = 0; c.dx = c.dy = 0; c.w00 = c.w01 = c.w10 = c.w11 = 0.f; c.lx = c.ly = 0.f;
         c.f00 = c.f01 = c.f10 = c.f11 = 0.f; c.valid = false;
         float a = 0.f;
@@ -372,7 +378,8 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
                 d[j][0] = v00.dot(g); d[j][1] = v01.dot(g); d[j][2] = v10.dot(g); d[j][3] = v11.dot(g);
             }
             // scatter w * a * g with 16 B reductions; zero-weight corners are skipped
-            if constexpr (!kPaired) {
+            if constexpr (!kScatter) {
+            } else if constexpr (!kPaired) {
                 float *gp = grad_value + o00;
                 if (q00 != 0.f) red_add_v4(gp, q00 * gra[0], q00 * gra[1], q00 * gra[2], q00 * gra[3]);
                 if (q01 != 0.f) red_add_v4(gp + ox, q01 * gra[0], q01 * gra[1], q01 * gra[2], q01 * gra[3]);
@@ -440,6 +447,10 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     }
 }
 
+
+}  // namespace bevf
+#include "msda_splat.cuh"
+namespace bevf {
 
 // ------------------------------------------------------------------------------------------------
 // any head_dim: one warp per (query, head) row, lanes stride over channels
@@ -556,7 +567,7 @@ static int check_dims(const char *who, int B, int S, int M, int D, int Q, int L,
     if ((long long)S * M * D >= (1ll << 31))
         return fail("%s: one batch item of value exceeds 2^31 elements", who);
     if ((long long)L * P * P >= 65536) return fail("%s: num_levels * num_points^2 must be < 65536", who);
-    return 0;
+    return 0;    // (level sizes are device data: H, W < 32768 is the caller's contract, see the header)
 }
 
 template <typename T, typename TO>
@@ -579,19 +590,69 @@ static int launch_fwd(const char *who, const void *value, const int64_t *hw, con
     return check_launch(who);
 }
 
+// BEVF_MSDA_BWD=fused selects the one-kernel backward (every corner contribution its own L2 reduction);
+// the default splits it into the gather half (grad_loc / grad_attn) and the register-merging splat
+// (grad_value).  BEVF_SPLAT_DIRECT is a bit mask of pyramid levels the splat never tries to merge.
+static int bwd_split_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BEVF_MSDA_BWD");
+        v = (e && e[0] == 'f') ? 0 : 1;
+    }
+    return v;
+}
+static unsigned splat_direct_mask() {
+    static long v = -1;
+    if (v < 0) {
+        const char *e = getenv("BEVF_SPLAT_DIRECT");
+        v = e ? strtol(e, nullptr, 0) : 0;
+    }
+    return (unsigned)v;
+}
+
+template <typename TG>
+static int launch_splat(const char *who, const float *loc, const float *attn, const void *go, float *gv,
+                        const int *row_map, const int *order, const int64_t *hw, const int64_t *ls,
+                        int S, int M, int Q, int L, int P, long long pairs, cudaStream_t st) {
+    const size_t smem = splat_smem_bytes(M, sizeof(TG));
+    static bool attr_done = false;                     // per instantiation
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(msda_bwd_splat_d32<TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)splat_smem_bytes(kSplatMaxHeads, sizeof(TG))) != cudaSuccess) {
+            cudaGetLastError();
+            return fail("%s: cannot reserve shared memory for the splat kernel", who);
+        }
+        attr_done = true;
+    }
+    const unsigned grid = (unsigned)((pairs + kSplatG - 1) / kSplatG);
+    msda_bwd_splat_d32<TG><<<grid, 32 * M, smem, st>>>(loc, attn, (const TG *)go, gv, row_map, order, hw,
+                                                       ls, S, M, Q, L, P, pairs, splat_direct_mask());
+    return check_launch(who);
+}
+
 template <typename T, typename TG>
 static int launch_bwd(const char *who, const void *value, const int64_t *hw, const int64_t *ls,
                       const float *loc, const float *attn, const void *go, float *gv, float *gl,
-                      float *ga, const int *row_map, int S, int M, int D, int Q, int L, int P,
-                      long long rows, cudaStream_t st) {
+                      float *ga, const int *row_map, const int *order, int S, int M, int D, int Q,
+                      int L, int P, long long rows, cudaStream_t st) {
     if (D == 32) {
         constexpr int G = Vec<T>::N;
         const int iters = pick_iters(rows, G);
         const long long per_block = (long long)(kThreads / 32) * G * iters;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
-        msda_bwd_d32<T, TG><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
-                                                       (const TG *)go, gv, gl, ga, row_map, S, M, Q,
-                                                       L, P, (65536 + P - 1) / P, iters, rows);
+        const bool split = bwd_split_enabled() && M <= kSplatMaxHeads && S * (long long)M * 32 < (1ll << 31);
+        if (split) {
+            if (int e = launch_splat<TG>(who, loc, attn, go, gv, row_map, order, hw, ls, S, M, Q, L, P,
+                                         rows / M, st))
+                return e;
+            msda_bwd_d32<T, TG, false><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
+                                                                  (const TG *)go, gv, gl, ga, row_map, S, M,
+                                                                  Q, L, P, (65536 + P - 1) / P, iters, rows);
+        } else {
+            msda_bwd_d32<T, TG, true><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
+                                                                 (const TG *)go, gv, gl, ga, row_map, S, M,
+                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows);
+        }
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
         msda_bwd_generic<T, TG><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
@@ -626,8 +687,8 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
                               const int64_t *level_hw, const int64_t *level_start, const float *loc,
                               const float *attn, const void *grad_out, int grad_out_dtype,
                               float *grad_value, float *grad_loc, float *grad_attn,
-                              const int *row_map, int B, int S, int M, int D, int Q, int L, int P,
-                              void *stream) {
+                              const int *row_map, const int *order, int B, int S, int M, int D, int Q,
+                              int L, int P, void *stream) {
     if (int e = check_dims(who, B, S, M, D, Q, L, P)) return e;
     const long long rows = (row_map ? 1ll : (long long)B) * Q * M;
     if (rows == 0) return 0;
@@ -641,9 +702,9 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
     const bool vb = value_dtype == BEVF_DTYPE_BF16, gb = grad_out_dtype == BEVF_DTYPE_BF16;
     if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (grad_out_dtype != BEVF_DTYPE_F32 && !gb))
         return fail("%s: unsupported dtype code", who);
-    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, S, M, D, Q, L, P, rows, st);
-    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, S, M, D, Q, L, P, rows, st);
-    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, S, M, D, Q, L, P, rows, st);
+    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st);
+    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st);
+    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st);
     return fail("%s: fp32 value with bf16 grad_out is not supported", who);
 }
 
@@ -666,7 +727,7 @@ extern "C" int bevf_msda_backward(const void *value, int value_dtype, const int6
                                   int Q, int L, int P, void *stream) {
     return msda_backward_impl("bevf_msda_backward", value, value_dtype, level_hw, level_start, loc,
                               attn, grad_out, grad_out_dtype, grad_value, grad_loc, grad_attn,
-                              nullptr, B, S, M, D, Q, L, P, stream);
+                              nullptr, nullptr, B, S, M, D, Q, L, P, stream);
 }
 
 extern "C" int bevf_msda_rows_forward(const void *value, int value_dtype, const int64_t *level_hw,
@@ -688,5 +749,18 @@ extern "C" int bevf_msda_rows_backward(const void *value, int value_dtype, const
     if (!row_map && R > 0) return fail("%s: row_map is null", "bevf_msda_rows_backward");
     return msda_backward_impl("bevf_msda_rows_backward", value, value_dtype, level_hw, level_start,
                               loc, attn, grad_out, grad_out_dtype, grad_value, grad_loc, grad_attn,
-                              row_map, B, S, M, D, R, L, P, stream);
+                              row_map, nullptr, B, S, M, D, R, L, P, stream);
+}
+
+extern "C" int bevf_msda_rows_backward_ordered(const void *value, int value_dtype, const int64_t *level_hw,
+                                               const int64_t *level_start, const float *loc,
+                                               const float *attn, const void *grad_out,
+                                               int grad_out_dtype, float *grad_value, float *grad_loc,
+                                               float *grad_attn, const int32_t *row_map,
+                                               const int32_t *group_order, int B, int S, int M, int D,
+                                               int R, int L, int P, void *stream) {
+    if (!row_map && R > 0) return fail("%s: row_map is null", "bevf_msda_rows_backward_ordered");
+    return msda_backward_impl("bevf_msda_rows_backward_ordered", value, value_dtype, level_hw,
+                              level_start, loc, attn, grad_out, grad_out_dtype, grad_value, grad_loc,
+                              grad_attn, row_map, group_order, B, S, M, D, R, L, P, stream);
 }

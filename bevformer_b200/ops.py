@@ -223,7 +223,9 @@ def msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_m
 
 
 def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
-                       grad_value=None):
+                       grad_value=None, group_order=None):
+    """``group_order`` (R,) int32: optional permutation of the rows in which runs of 64 entries are
+    spatial neighbours on one value map (see bevf_msda_rows_backward_ordered)."""
     for t, n in ((value, "value"), (loc, "sampling_loc"), (attn, "attn_weight"),
                  (row_map, "row_map"), (grad_output, "grad_output")):
         _need_cuda(t, n)
@@ -236,12 +238,15 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
     lib = _lib.load()
     with torch.cuda.device(value.device), _timed("msda_rows_backward", value.device, (R, L)):
-        st = lib.bevf_msda_rows_backward(value.data_ptr(), _DT[value.dtype], ss.data_ptr(),
-                                         ls.data_ptr(), loc.data_ptr(), attn.data_ptr(),
-                                         grad_output.data_ptr(), _DT[grad_output.dtype],
-                                         grad_value.data_ptr(), grad_loc.data_ptr(),
-                                         grad_attn.data_ptr(), row_map.data_ptr(),
-                                         NB, S, M, D, R, L, P, _stream_ptr(value))
+        if group_order is not None and (group_order.dtype != torch.int32 or group_order.numel() != R
+                                        or not group_order.is_cuda):
+            raise RuntimeError("group_order must be a CUDA int32 tensor with one entry per row")
+        st = lib.bevf_msda_rows_backward_ordered(value.data_ptr(), _DT[value.dtype], ss.data_ptr(),
+                                                 ls.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                                                 grad_output.data_ptr(), _DT[grad_output.dtype],
+                                                 grad_value.data_ptr(), grad_loc.data_ptr(),
+                                                 grad_attn.data_ptr(), row_map.data_ptr(), _ptr(group_order),
+                                                 NB, S, M, D, R, L, P, _stream_ptr(value))
     _lib.check(st, lib)
     return grad_value, grad_loc, grad_attn
 
@@ -250,19 +255,21 @@ class SamplerRows(Function):
     """Sampler over a compact list of query rows (SCA's in-view (camera, query) pairs)."""
 
     @staticmethod
-    def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index):
+    def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index, group_order=None):
         if value.dtype == torch.float16:      # the reference widens half inputs (…function.py:93)
             value = value.float()
         out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
+        ctx.group_order = group_order
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
         value, loc, attn, row_map, ss, ls = ctx.saved_tensors
-        gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous())
-        return gv.to(value.dtype), gl, ga, None, None, None
+        gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(),
+                                        group_order=ctx.group_order)
+        return gv.to(value.dtype), gl, ga, None, None, None, None
 
 
 def sca_prep_forward(raw, ref_cam, pair_q, pair_cam, level_hw, B, Nq, M, L, P):

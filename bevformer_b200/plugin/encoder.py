@@ -270,7 +270,8 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                 if fuse and isinstance(att, TemporalSelfAttention) and att.batch_first:
                     q_in = q_in0 if i == 0 else None
                     pre = att.attend(query, prev_bev, bev_pos, query_key_padding_mask, ref_2d,
-                                     tsa_ss, tsa_lsi, q_in=q_in)
+                                     tsa_ss, tsa_lsi, q_in=q_in,
+                                     bev_hw=None if bev_h is None else (bev_h, bev_w))
                     query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1

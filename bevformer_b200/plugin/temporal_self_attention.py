@@ -83,7 +83,8 @@ class TemporalSelfAttention(nn.Module):
 
     # -------------------------------------------------------------------------------------------
     def attend(self, query, value=None, query_pos=None, key_padding_mask=None,
-               reference_points=None, spatial_shapes=None, level_start_index=None, q_in=None):
+               reference_points=None, spatial_shapes=None, level_start_index=None, q_in=None,
+               bev_hw=None):
         """Everything up to and including output_proj, batch-first, WITHOUT dropout / identity.
         query (bs, Nq, C); value (bs*2, Nq, C) stacked [prev, cur] or None; ``q_in`` = query +
         query_pos when the caller already has it (the encoder's previous LayerNorm emits it)."""
@@ -115,7 +116,11 @@ class TemporalSelfAttention(nn.Module):
                 # reduction kernel forward, no scatter of the gradient to the two frames backward
                 loc, attn = tsa_sampling_head(q_cat, w, b, ref, ss.contiguous(), bs, nq, self.num_heads,
                                               self.num_levels, self.num_points, True)
-                out = ops.SamplerRows.apply(v, loc, attn, self._frame_map(bs, nq, query.device), ss, lsi)
+                order = None
+                if bev_hw is not None and bev_hw[0] * bev_hw[1] == nq:
+                    order = self._group_order(bs, int(bev_hw[0]), int(bev_hw[1]), query.device)
+                out = ops.SamplerRows.apply(v, loc, attn, self._frame_map(bs, nq, query.device), ss, lsi,
+                                            order)
                 w2 = torch.cat([self.output_proj.weight, self.output_proj.weight], 1) * 0.5
                 return linear(out.view(bs, nq, 2 * c), w2, self.output_proj.bias)
             loc, attn = tsa_sampling_head(q_cat, w, b, ref, ss.contiguous(), bs, nq, self.num_heads,
@@ -140,6 +145,27 @@ class TemporalSelfAttention(nn.Module):
         if key not in cache:
             r = torch.arange(bs * nq * 2, device=device, dtype=torch.int32)
             cache[key] = ((r // (2 * nq)) * 2 + (r % 2)).contiguous()
+        return cache[key]
+
+    def _group_order(self, bs, h, w, device, tile=8):
+        """Permutation of the interleaved sampler rows (b, q, frame) in which 64 consecutive entries are
+        one 8x8 BEV tile of one frame: the rows whose grad_value contributions the backward merges
+        before they reach L2 (bevf_msda_rows_backward_ordered).  Cached per shape."""
+        key = ("order", bs, h, w, str(device))
+        cache = self.__dict__.setdefault("_frame_map_cache", {})
+        if key not in cache:
+            qi = torch.arange(h, device=device).view(h, 1).expand(h, w)
+            qj = torch.arange(w, device=device).view(1, w).expand(h, w)
+            tiles_x = (w + tile - 1) // tile
+            tkey = ((qi // tile) * tiles_x + qj // tile) * (tile * tile) + (qi % tile) * tile + qj % tile
+            q_sorted = torch.argsort(tkey.reshape(-1), stable=True)                # queries in tile order
+            tile_of = (tkey.reshape(-1)[q_sorted] // (tile * tile))
+            # within a tile: all its queries for frame 0, then for frame 1
+            k2 = (tile_of * 2).repeat_interleave(2) + torch.arange(2, device=device).repeat(h * w)
+            rows = (q_sorted.repeat_interleave(2) * 2 + torch.arange(2, device=device).repeat(h * w))
+            rows = rows[torch.argsort(k2, stable=True)]
+            full = (torch.arange(bs, device=device).view(bs, 1) * (2 * h * w) + rows.view(1, -1)).reshape(-1)
+            cache[key] = full.to(torch.int32).contiguous()
         return cache[key]
 
     def _box_points(self, raw, reference_points, bs, nq):

@@ -122,6 +122,22 @@ BEVF_API int bevf_msda_rows_backward(const void *value, int value_dtype, const i
                                      const int32_t *row_map, int B, int S, int M, int D, int R,
                                      int L, int P, void *stream);
 
+/*
+ * Same as bevf_msda_rows_backward, plus `group_order` (R,) int32 (or NULL = identity): a permutation of
+ * the rows that lists them so that runs of 64 consecutive entries are spatial neighbours on ONE value map
+ * (for the interleaved TSA rows: 8x8 BEV tiles of one frame).  The grad_value half of the backward
+ * merges the contributions of such a run in registers before they reach L2 (csrc/msda_splat.cuh); the
+ * order changes which additions are merged, never the result beyond fp32 summation order.
+ * Level maps must satisfy H_l, W_l < 32768.
+ */
+BEVF_API int bevf_msda_rows_backward_ordered(const void *value, int value_dtype, const int64_t *level_hw,
+                                             const int64_t *level_start, const float *loc,
+                                             const float *attn, const void *grad_out,
+                                             int grad_out_dtype, float *grad_value, float *grad_loc,
+                                             float *grad_attn, const int32_t *row_map,
+                                             const int32_t *group_order, int B, int S, int M, int D,
+                                             int R, int L, int P, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused memory-bound pieces of one encoder layer.  "raw" is the fp32 output of the layer's combined
  * sampling_offsets|attention_weights GEMM, one row per BEV query.

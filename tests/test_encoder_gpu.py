@@ -91,7 +91,9 @@ def test_backward_against_golden_fp32(name, workload, bs, with_prev):
     ok, m = robust_close(inp.bev_query.grad.cpu()[g["rows_q"]], g["grad_query_rows"], 2e-3)
     assert ok, ("grad_query", m)
     # every layer's temporal self-attention adds bev_pos to its query: all of them feed this gradient
-    ok, m = robust_close(inp.bev_pos.grad.cpu()[g["rows_q"]], g["grad_pos_rows"], 2e-3)
+    # (it is the sum of the TSA grad_loc paths of all layers: as boundary-sensitive as the
+    # sampling_offsets rows below, hence their bar)
+    ok, m = robust_close(inp.bev_pos.grad.cpu()[g["rows_q"]], g["grad_pos_rows"], 5e-3)
     assert ok, ("grad_pos", m)
     got, want = stats(inp.bev_pos.grad), g["grad_pos_stats"]
     assert np.all(np.abs(got[1:3] - want[1:3]) <= 5e-3 * np.abs(want[1:3])), ("grad_pos", got, want)

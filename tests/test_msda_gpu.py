@@ -151,7 +151,7 @@ def test_base_shapes_properties(which):
     assert rel_err(ga.cpu(), rga) < 1e-3 and rel_err(gl.cpu(), rgl) < 1e-3
 
 
-@pytest.mark.parametrize("which", ["sca", "tsa"])
+@pytest.mark.parametrize("which", ["sca", "tsa", "tsa_rows"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_base_rig_geometry_against_oracle(which, dtype):
     """The launches the headline benchmark times: base shapes on the REAL geometry (SCA: the 44 511
@@ -159,10 +159,13 @@ def test_base_rig_geometry_against_oracle(which, dtype):
     points; TSA: 2 x 40 000 rows around each query's own cell), forward and backward, fp32 and bf16
     storage, every output element against Oracle-S on the same (storage-rounded) inputs.
     Bars: 1e-3 fp32 / 1e-2 bf16 (BASELINE.json north_star)."""
-    from tools.bench_msda import rig_sca_inputs, rig_tsa_inputs
+    from tools.bench_msda import rig_sca_inputs, rig_tsa_inputs, rig_tsa_rows_inputs
     tol = TOL[dtype]
+    order = None
     if which == "sca":
         v, ss, lsi, loc, attn, row_map = rig_sca_inputs(DEV)
+    elif which == "tsa_rows":     # the encoder's TSA launch: interleaved (b, q, frame) rows + 8x8-tile group order
+        v, ss, lsi, loc, attn, row_map, order = rig_tsa_rows_inputs(DEV)
     else:
         v, ss, lsi, loc, attn = rig_tsa_inputs(DEV)
         row_map = None
@@ -171,7 +174,7 @@ def test_base_rig_geometry_against_oracle(which, dtype):
     gout = fixed_projection((nrows, 256)).to(DEV, dtype)
     if row_map is not None:
         out = ops.msda_rows_forward(vd, ss, lsi, loc, attn, row_map)
-        gv, gl, ga = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout)
+        gv, gl, ga = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout, group_order=order)
     else:
         out = ops.msda_forward(vd, ss, lsi, loc, attn)
         gv, gl, ga = ops.msda_backward(vd, ss, lsi, loc, attn, gout.view(out.shape))

@@ -48,6 +48,29 @@ def rig_sca_inputs(dev):
     return value, ss, lsi, loc, attn, plan.row_map
 
 
+def rig_tsa_rows_inputs(dev):
+    """TSA as the encoder launches it: interleaved rows (b, q, frame) through the row-list entry points,
+    with the 8x8-tile group order for the backward's merge."""
+    from bevformer_b200.plugin.temporal_self_attention import TemporalSelfAttention
+    w = syn.WORKLOADS["base"]
+    sd = syn.make_state_dict(w)
+    g = torch.Generator().manual_seed(0)
+    nq, m, p = w.num_query, 8, 4
+    from bevformer_b200 import ops as _ops
+    raw = torch.cat([sd["layers.0.attentions.0.sampling_offsets.bias"].view(1, -1)
+                     + 0.5 * torch.randn(nq, m * 2 * p * 2, generator=g),
+                     torch.randn(nq, m * 2 * p, generator=g)], 1).to(dev).contiguous()
+    ys, xs = torch.meshgrid(torch.arange(200.0), torch.arange(200.0), indexing="ij")
+    ref = torch.stack([(xs + 0.5) / 200, (ys + 0.5) / 200], -1).reshape(1, nq, 1, 2)
+    ref = torch.cat([ref + torch.tensor([0.01, -0.02]), ref], 0).to(dev).contiguous()
+    ss = torch.tensor([[200, 200]], dtype=torch.int64, device=dev)
+    lsi = torch.zeros(1, dtype=torch.int64, device=dev)
+    loc, attn = _ops.tsa_prep_forward(raw, ref, ss, 1, nq, m, 1, p, True)
+    value = torch.randn(2, nq, 8, 32, generator=g).to(dev)
+    tsa = TemporalSelfAttention()
+    return value, ss, lsi, loc, attn, tsa._frame_map(1, nq, torch.device(dev)), tsa._group_order(1, 200, 200, torch.device(dev))
+
+
 def rig_tsa_inputs(dev):
     w = syn.WORKLOADS["base"]
     sd = syn.make_state_dict(w)
@@ -100,7 +123,7 @@ def main():
     hbm = peaks.get("hbm_gbs", 6650.0)
     res = []
     for name, sh in shapes.items():
-        if args.only and args.only not in name:
+        if args.only and not any(o and o in name for o in args.only.split(",")):
             continue
         v, ss, lsi, loc, attn = syn.make_msda_inputs(sh["bs"], sh["levels"], sh["nq"], 8, 32,
                                                      sh["pts"], seed=0, device=dev)
@@ -128,12 +151,15 @@ def main():
             print(json.dumps(r), flush=True)
             res.append(r)
     # ---- the same kernels on the real geometry (what the encoder actually launches)
-    for name in ("sca_rig", "tsa_rig"):
-        if args.only and args.only not in name:
+    for name in ("sca_rig", "tsa_rig", "tsa_rows"):
+        if args.only and not any(o and o in name for o in args.only.split(",")):
             continue
+        order = None
         if name == "sca_rig":
             v, ss, lsi, loc, attn, row_map = rig_sca_inputs(dev)
             R = loc.shape[0]
+        elif name == "tsa_rows":
+            v, ss, lsi, loc, attn, row_map, order = rig_tsa_rows_inputs(dev)
         else:
             v, ss, lsi, loc, attn = rig_tsa_inputs(dev)
             row_map = None
@@ -151,7 +177,7 @@ def main():
             g = torch.randn_like(out)
             gv = torch.zeros(v.shape, device=dev, dtype=torch.float32)
             if row_map is not None:
-                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv)
+                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order)
             else:
                 bwd = lambda: ops.msda_backward(vd, ss, lsi, loc, attn, g, gv)
             if args.profile:
@@ -162,14 +188,16 @@ def main():
             C = M * 32
             bf = B * S * C * sz + nrows * M * L * P * 12 + nrows * C * sz
             bb = bf + B * S * C * 4 + nrows * M * L * P * 12
-            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], fwd_ms=round(t_f, 4),
+            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], bwd_mode=os.environ.get("BEVF_MSDA_BWD", "split"),
+                     splat_direct=os.environ.get("BEVF_SPLAT_DIRECT", "0"), fwd_ms=round(t_f, 4),
                      bwd_ms=round(t_b, 4), fwd_alg_MB=round(bf / 1e6, 1), bwd_alg_MB=round(bb / 1e6, 1),
                      fwd_GBs=round(bf / t_f / 1e6, 1), bwd_GBs=round(bb / t_b / 1e6, 1),
                      fwd_frac=round(bf / t_f / 1e6 / hbm, 4), bwd_frac=round(bb / t_b / 1e6 / hbm, 4))
             print(json.dumps(r), flush=True)
             res.append(r)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/bench_msda.json", "w"), indent=1)
+    tag = os.environ.get("BENCH_TAG", "")
+    json.dump(res, open(f"gpurun_out/bench_msda{tag}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":

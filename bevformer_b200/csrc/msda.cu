@@ -590,14 +590,18 @@ static int launch_fwd(const char *who, const void *value, const int64_t *hw, con
     return check_launch(who);
 }
 
-// BEVF_MSDA_BWD=fused selects the one-kernel backward (every corner contribution its own L2 reduction);
-// the default splits it into the gather half (grad_loc / grad_attn) and the register-merging splat
-// (grad_value).  BEVF_SPLAT_DIRECT is a bit mask of pyramid levels the splat never tries to merge.
+// Backward mode.  0 = one kernel (default): every corner contribution is its own 16 B-vector L2 reduction.
+// 1 = split: gather half (grad_loc / grad_attn) + the register-merging splat kernel of msda_splat.cuh
+// (grad_value).  The split removes 82 % of the L2 reductions but costs 2.3x the instructions and measured
+// slower on B200 (profiles/README.md, r2c): it stays selectable for A/B runs -- environment
+// BEVF_MSDA_BWD=split or bevf_msda_set_backward_mode(1).
+static std::atomic<int> g_bwd_mode{-1};
 static int bwd_split_enabled() {
-    static int v = -1;
+    int v = g_bwd_mode.load(std::memory_order_relaxed);
     if (v < 0) {
         const char *e = getenv("BEVF_MSDA_BWD");
-        v = (e && e[0] == 'f') ? 0 : 1;
+        v = (e && e[0] == 's') ? 1 : 0;
+        g_bwd_mode.store(v, std::memory_order_relaxed);
     }
     return v;
 }
@@ -750,6 +754,12 @@ extern "C" int bevf_msda_rows_backward(const void *value, int value_dtype, const
     return msda_backward_impl("bevf_msda_rows_backward", value, value_dtype, level_hw, level_start,
                               loc, attn, grad_out, grad_out_dtype, grad_value, grad_loc, grad_attn,
                               row_map, nullptr, B, S, M, D, R, L, P, stream);
+}
+
+extern "C" int bevf_msda_set_backward_mode(int mode) {
+    if (mode != 0 && mode != 1) return fail("%s: mode must be 0 (one kernel) or 1 (split)", "bevf_msda_set_backward_mode");
+    g_bwd_mode.store(mode, std::memory_order_relaxed);
+    return 0;
 }
 
 extern "C" int bevf_msda_rows_backward_ordered(const void *value, int value_dtype, const int64_t *level_hw,

@@ -138,6 +138,15 @@ BEVF_API int bevf_msda_rows_backward_ordered(const void *value, int value_dtype,
                                              const int32_t *group_order, int B, int S, int M, int D,
                                              int R, int L, int P, void *stream);
 
+/*
+ * Selects how bevf_msda_*backward* computes grad_value (process-wide; default 0, or the environment
+ * variable BEVF_MSDA_BWD=split).  0: one kernel, one 16 B-vector L2 reduction per corner contribution.
+ * 1: gather kernel + a splat kernel that merges the contributions of 64 neighbouring rows in registers
+ * before they reach L2 (fewer reductions, more instructions; kept for A/B measurements).
+ * Results agree up to fp32 summation order.
+ */
+BEVF_API int bevf_msda_set_backward_mode(int mode);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused memory-bound pieces of one encoder layer.  "raw" is the fp32 output of the layer's combined
  * sampling_offsets|attention_weights GEMM, one row per BEV query.

@@ -62,7 +62,7 @@ def test_head_dims_against_oracle(dim):
     dict(bs=6, levels=[(15, 25)], nq=592, heads=8, pts=8),        # tiny's SCA shape (max_len 592)
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_shapes_against_oracle(shape, dtype):
+def test_shapes_against_oracle(shape, dtype, backward_mode):
     v, ss, lsi, loc, attn = syn.make_msda_inputs(shape["bs"], shape["levels"], shape["nq"],
                                                  shape["heads"], 32, shape["pts"], seed=2,
                                                  loc_range=(-0.2, 1.2))
@@ -151,9 +151,19 @@ def test_base_shapes_properties(which):
     assert rel_err(ga.cpu(), rga) < 1e-3 and rel_err(gl.cpu(), rgl) < 1e-3
 
 
+@pytest.fixture(params=[0, 1], ids=["bwd_one_kernel", "bwd_split"])
+def backward_mode(request):
+    """Both grad_value strategies of the library (bevf_msda_set_backward_mode) must pass the same bars."""
+    from bevformer_b200 import _lib
+    lib = _lib.load()
+    assert lib.bevf_msda_set_backward_mode(request.param) == 0
+    yield request.param
+    lib.bevf_msda_set_backward_mode(0)
+
+
 @pytest.mark.parametrize("which", ["sca", "tsa", "tsa_rows"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_base_rig_geometry_against_oracle(which, dtype):
+def test_base_rig_geometry_against_oracle(which, dtype, backward_mode):
     """The launches the headline benchmark times: base shapes on the REAL geometry (SCA: the 44 511
     in-view (camera, query) pairs of the synthetic rig, 4 levels, 8 points, through the row-list entry
     points; TSA: 2 x 40 000 rows around each query's own cell), forward and backward, fp32 and bf16

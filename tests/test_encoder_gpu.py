@@ -148,13 +148,13 @@ def test_backward_bf16_tracks_fp32_reference(name, workload):
         report[key] = (round(_cos(got, want), 5), round(l2, 4))
     print(name, report)
     for key, (cos, l2) in report.items():
-        assert cos > 0.98 and l2 < 0.2, (key, cos, l2)
+        assert cos > 0.99 and l2 < 0.12, (key, cos, l2)   # measured on B200: base 0.996 / 0.088, toy 0.999 / 0.05
     worst = (None, 0.0)
     for k, p in enc.named_parameters():
         got, ref = stats(p.grad.float()), g["gstat:" + k]
         dev = abs(got[2] - ref[2]) / max(ref[2], 1e-12)
         worst = max(worst, (k, dev), key=lambda t: t[1])
-        assert dev <= 0.15, (k, got, ref)                                   # sum of squares
+        assert dev <= 0.10, (k, got, ref)                                   # sum of squares (measured: <= 0.06)
         if "gfull:" + k in g.files:                                         # small tensors: element-wise direction
             assert _cos(p.grad.float().cpu(), g["gfull:" + k]) > 0.97, k
     print(name, "worst parameter-gradient energy deviation", worst)

@@ -33,6 +33,7 @@ sca_prep_fwd(const float *__restrict__ raw, const float *__restrict__ ref_cam,
     const long long br = t / M;
     const int r = (int)(br % R), b = (int)(br / R);
     const int q = pair_q[r], cam = pair_cam[r];
+    if (q < 0) return;                                // unused row of a fixed-capacity pair list
     const int LP = L * P, nout = M * LP * 3;
     const float *rq = raw + ((long long)b * Nq + q) * nout;
     const float *off = rq + (long long)m * LP * 2;
@@ -199,6 +200,7 @@ sca_prep_fwd_m8(const float *__restrict__ raw, const float *__restrict__ ref_cam
     if (t >= (long long)B * R) return;
     const int r = (int)(t % R), b = (int)(t / R);
     const int q = __ldg(pair_q + r), cam = __ldg(pair_cam + r);
+    if (q < 0) return;                                // unused row of a fixed-capacity pair list (warp-uniform)
     const int LP = 4 * PPL, k0 = sub * PPL;
     const float *rq = raw + ((long long)b * Nq + q) * (M * LP * 3);
     float lg[PPL], off[2 * PPL];
@@ -739,6 +741,7 @@ sca_combine_bwd(const T *__restrict__ g_slots, const int *__restrict__ pair_q,
     const long long br = t / per_row;
     const int r = (int)(br % R), b = (int)(br / R);
     const int q = __ldg(pair_q + r);
+    if (q < 0) return;                                // unused row of a fixed-capacity pair list
     const float ic = inv_count[(long long)b * Nq + q];
     float v[VEC];
     load_vec<T, VEC>(g_slots + ((long long)b * Nq + q) * C + cv * VEC, v);

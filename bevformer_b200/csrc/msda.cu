@@ -198,10 +198,11 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     for (int it = 0; it < iters; ++it) {
     long long row = (((long long)blockIdx.x * (kThreads / 32) + warp) * iters + it) * G + grp;
     if (row - grp >= rows) break;                 // warp-uniform
-    const bool live = row < rows;                 // dead groups still take part in the shuffles
+    bool live = row < rows;                       // dead groups still take part in the shuffles
     if (!live) row = rows - 1;
     const int m = (int)(row % M);
-    const int b = value_map_of(row_map, row, M, Q);
+    int b = value_map_of(row_map, row, M, Q);
+    if (b < 0) { live = false; b = 0; }           // row_map -1: unused row of a fixed-capacity list
     const int pix = M * 32;
     const int LP = L * P;
     const T *vbase = value + ((long long)b * S * M + m) * 32 + sub * VEC;
@@ -287,10 +288,11 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     for (int it = 0; it < iters; ++it) {
     long long row = (((long long)blockIdx.x * (kThreads / 32) + warp) * iters + it) * G + grp;
     if (row - grp >= rows) break;                 // warp-uniform
-    const bool live = row < rows;
+    bool live = row < rows;
     if (!live) row = rows - 1;
     const int m = (int)(row % M);
-    const int b = value_map_of(row_map, row, M, Q);
+    int b = value_map_of(row_map, row, M, Q);
+    if (b < 0) { live = false; b = 0; }           // row_map -1: unused row of a fixed-capacity list
     const int pix = M * 32;
     const int LP = L * P;
     const long long voff = ((long long)b * S * M + m) * 32 + sub * VEC;
@@ -469,6 +471,7 @@ msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_
     if (row >= rows) return;
     const int m = (int)(row % M);
     const int b = value_map_of(row_map, row, M, Q);
+    if (b < 0) return;                            // unused row (whole warp)
     const long long pix = (long long)M * D;
     for (int c0 = lane; c0 < D; c0 += 32) {
         float acc = 0.f;
@@ -504,6 +507,7 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ level_
     if (row >= rows) return;   // whole warp leaves together
     const int m = (int)(row % M);
     const int b = value_map_of(row_map, row, M, Q);
+    if (b < 0) return;         // unused row (whole warp)
     const long long pix = (long long)M * D;
     for (int l = 0; l < L; ++l) {
         const int H = s_h[l], W = s_w[l];

@@ -81,8 +81,9 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
         const long long idx = gb + k;
         long long r = -1;
         if (idx < pairs) r = order ? (long long)__ldg(order + idx) : idx;
-        row_s[k] = (int)r;
-        map_s[k] = r < 0 ? -1 : (row_map ? __ldg(row_map + r) : (int)(r / Q));
+        const int mp = r < 0 ? -1 : (row_map ? __ldg(row_map + r) : (int)(r / Q));
+        row_s[k] = mp < 0 ? -1 : (int)r;                  // row_map -1: unused row of a fixed-capacity list
+        map_s[k] = mp;
     }
     load_level_tab(level_hw, level_start, L, C, tab);                              // ends with __syncthreads()
     {   // the CTA's grad_out tile, in its storage type

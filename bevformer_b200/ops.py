@@ -531,8 +531,34 @@ class ScaCombine(Function):
         return g_out, None, None, None, None, None
 
 
-def point_sampling(lidar2img, pc_range, z_norm, img_h, img_w, bev_h, bev_w):
-    """lidar2img (B, ncam, 4, 4) f32 CUDA -> ref_cam (ncam,B,Nq,D,2) f32, bev_mask (ncam,B,Nq,D) bool."""
+def sca_plan_build(mask_u8, qorder, capacity):
+    """Device-side pair list (bevf_sca_plan_build): mask_u8 (ncam, B, Nq, D) uint8, qorder (Nq,) int32 or
+    None -> dict of the plan tensors; no host synchronisation."""
+    _need_cuda(mask_u8, "bev_mask")
+    if mask_u8.dtype != torch.uint8:
+        raise RuntimeError("bev_mask must be uint8")
+    ncam, B, Nq, D = mask_u8.shape
+    dev = mask_u8.device
+    lib = _lib.load()
+    i32 = dict(device=dev, dtype=torch.int32)
+    out = dict(pair_q=torch.empty(capacity, **i32), pair_cam=torch.empty(capacity, **i32),
+               pair_of=torch.empty((ncam, Nq), **i32), row_map=torch.empty(B * capacity, **i32),
+               inv_count=torch.empty((B, Nq), device=dev, dtype=torch.float32),
+               counters=torch.empty(2, **i32))
+    ws = torch.empty(int(lib.bevf_sca_plan_workspace_ints(ncam, Nq)), **i32)
+    with torch.cuda.device(dev):
+        st = lib.bevf_sca_plan_build(mask_u8.data_ptr(), _ptr(qorder), out["pair_q"].data_ptr(),
+                                     out["pair_cam"].data_ptr(), out["pair_of"].data_ptr(),
+                                     out["row_map"].data_ptr(), out["inv_count"].data_ptr(),
+                                     out["counters"].data_ptr(), ws.data_ptr(), B, ncam, Nq, D,
+                                     int(capacity), _stream_ptr(mask_u8))
+    _lib.check(st, lib)
+    return out
+
+
+def point_sampling(lidar2img, pc_range, z_norm, img_h, img_w, bev_h, bev_w, raw_mask=False):
+    """lidar2img (B, ncam, 4, 4) f32 CUDA -> ref_cam (ncam,B,Nq,D,2) f32, bev_mask (ncam,B,Nq,D) bool
+    (uint8 with ``raw_mask``: what the device-side plan builder reads)."""
     _need_cuda(lidar2img, "lidar2img")
     import ctypes
     B, ncam = lidar2img.shape[:2]
@@ -549,7 +575,7 @@ def point_sampling(lidar2img, pc_range, z_norm, img_h, img_w, bev_h, bev_w):
                                      mask.data_ptr(), B, ncam, bev_h, bev_w, D,
                                      _stream_ptr(lidar2img))
     _lib.check(st, lib)
-    return ref_cam, mask.bool()
+    return ref_cam, (mask if raw_mask else mask.bool())
 
 
 def linear_tc(x, weight, bias=None, residual=None, relu=False, out_dtype=None):

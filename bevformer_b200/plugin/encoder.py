@@ -393,24 +393,83 @@ class BEVFormerEncoder(nn.Module):
                 & (xy[..., 0:1] < 1.0) & (xy[..., 0:1] > 0.0)).squeeze(-1)
         return xy, mask
 
-    def _camera_geometry(self, bs, bev_h, bev_w, img_metas, device):
-        """reference_points_cam (cam, bs, Nq, D, 2) f32 and bev_mask (cam, bs, Nq, D) bool through
-        the fused projection kernel (replaces get_reference_points('3d') + point_sampling)."""
-        l2i = torch.as_tensor(np.asarray([m["lidar2img"] for m in img_metas], dtype=np.float32))
-        l2i = l2i.to(device, non_blocking=True).contiguous()                    # (B, cam, 4, 4)
+    def _camera_geometry(self, bs, bev_h, bev_w, img_metas, device, lidar2img=None, raw_mask=False):
+        """reference_points_cam (cam, bs, Nq, D, 2) f32 and bev_mask (cam, bs, Nq, D) through the fused
+        projection kernel (replaces get_reference_points('3d') + point_sampling).  ``lidar2img``: an
+        already-resident (bs, cam, 4, 4) f32 device tensor (what a CUDA-graph-captured step reads, refreshed
+        by the caller every frame); otherwise the matrices are copied from ``img_metas``."""
+        if lidar2img is None:
+            l2i = torch.as_tensor(np.asarray([m["lidar2img"] for m in img_metas], dtype=np.float32))
+            l2i = l2i.to(device, non_blocking=True).contiguous()                # (B, cam, 4, 4)
+        else:
+            l2i = lidar2img.to(device=device, dtype=torch.float32).contiguous()
         z_extent = self.pc_range[5] - self.pc_range[2]
         z_norm = (torch.linspace(0.5, z_extent - 0.5, self.num_points_in_pillar) / z_extent).tolist()
         h, w = img_metas[0]["img_shape"][0][0], img_metas[0]["img_shape"][0][1]   # quirk 10
-        return ops.point_sampling(l2i, self.pc_range, z_norm, h, w, bev_h, bev_w)
+        return ops.point_sampling(l2i, self.pc_range, z_norm, h, w, bev_h, bev_w, raw_mask=raw_mask)
 
-    def prepare(self, img_metas, bev_h, bev_w, device) -> ScaPlan:
-        """Everything of a forward that depends only on the camera rig: pillar projection, in-view
-        mask, the (camera, query) pair plan.  This is the part with the host copy of lidar2img and the
-        one host sync; callers with a static rig (or a CUDA-graph-captured step) run it once and pass
-        the result as ``sca_plan=``."""
+    def prepare(self, img_metas, bev_h, bev_w, device, lidar2img=None) -> ScaPlan:
+        """Everything of a forward that depends only on the camera rig: pillar projection, in-view mask,
+        the (camera, query) pair plan -- all on the device.  The first call for a BEV size synchronises
+        ONCE to size the pair list (capacity = pairs found + 15 %); every later call, and every call made
+        while a CUDA graph is being captured, is sync-free.  ``forward`` calls this itself unless a plan
+        is passed as ``sca_plan=``."""
+        device = torch.device(device)
         bs = len(img_metas)
-        ref_cam, bev_mask = self._camera_geometry(bs, bev_h, bev_w, img_metas, torch.device(device))
-        return ScaPlan.build(bev_mask, ref_cam, (bev_h, bev_w))
+        ref_cam, mask = self._camera_geometry(bs, bev_h, bev_w, img_metas, device, lidar2img, raw_mask=True)
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        key = (bev_h, bev_w, str(device))
+        if key not in cache:
+            cache[key] = dict(qorder=ScaPlan.tile_order(bev_h, bev_w, device), capacity=None, last=None)
+        ent = cache[key]
+        self._poll_plan(ent)
+        if ent["capacity"] is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("BEVFormerEncoder: run one eager forward (or prepare()) before capturing a "
+                                   "CUDA graph, so that the SCA pair list can be sized")
+            found = int((mask[:, 0] != 0).any(-1).sum())            # the one calibration sync
+            ent["capacity"] = max(256, -(-int(found * 1.15 + 64) // 256) * 256)
+        plan = ScaPlan.build_device(mask, ref_cam, ent["qorder"], ent["capacity"])
+        if not torch.cuda.is_current_stream_capturing():
+            # overflow is checked WITHOUT blocking: the counters travel to pinned memory behind an event
+            # and are looked at by the next prepare() / check_plan()
+            host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+            host.copy_(plan.counters, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            ent["last"] = (ev, host)
+        return plan
+
+    @staticmethod
+    def _poll_plan(ent, wait=False):
+        last = ent.get("last")
+        if last is None:
+            return
+        ev, host = last
+        if wait:
+            ev.synchronize()
+        if not ev.query():
+            return
+        ent["last"] = None
+        found, over = int(host[0]), int(host[1])
+        if over:
+            cap = ent["capacity"]
+            ent["capacity"] = max(256, -(-int(found * 1.15 + 64) // 256) * 256)
+            raise RuntimeError(f"BEVFormerEncoder: the camera rig put {found} (camera, query) pairs in view, more "
+                               f"than the pair-list capacity {cap}; the previous forward dropped the excess. "
+                               f"Capacity is now {ent['capacity']}: re-run the step (re-capture a captured graph)")
+
+    def check_plan(self, plan: Optional[ScaPlan] = None) -> Optional[int]:
+        """Blocking check of the pair-list capacity (tests, end of an epoch, after graph replays): raises
+        if a forward overflowed; returns the pair count of ``plan`` when one is given."""
+        for ent in self.__dict__.get("_plan_cache", {}).values():
+            self._poll_plan(ent, wait=True)
+        if plan is not None and plan.counters is not None:
+            found, over = (int(v) for v in plan.counters.tolist())
+            if over:
+                raise RuntimeError(f"SCA pair list overflow: {found} pairs > capacity {plan.num_pairs}")
+            return found
+        return None
 
     def _constants(self, bev_h, bev_w, bs, dev):
         """Small device tensors that never change for a BEV size (built once: creating a tensor from
@@ -435,16 +494,12 @@ class BEVFormerEncoder(nn.Module):
         dev, dtype = bev_query.device, bev_query.dtype
         ref_2d, tsa_ss, tsa_lsi = self._constants(bev_h, bev_w, bs, dev)
         plan = kwargs.pop("sca_plan", None)
+        l2i_dev = kwargs.pop("lidar2img", None)        # optional device-resident (bs, cam, 4, 4) matrices
         bev_mask = None
         if plan is None:
-            if dev.type == "cuda":
-                ref_cam, bev_mask = self._camera_geometry(bs, bev_h, bev_w, kwargs["img_metas"], dev)
-            else:
-                ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
-                                                   self.num_points_in_pillar, dim="3d", bs=bs,
-                                                   device=dev, dtype=dtype)
-                ref_cam, bev_mask = self.point_sampling(ref_3d, self.pc_range, kwargs["img_metas"])
-            plan = ScaPlan.build(bev_mask, ref_cam, (bev_h, bev_w))
+            if dev.type != "cuda":
+                raise RuntimeError("BEVFormerEncoder: bevformer_b200 has no CPU path")
+            plan = self.prepare(kwargs["img_metas"], bev_h, bev_w, dev, l2i_dev)
         ref_cam = plan.ref_cam
         if self.training and dev.type == "cuda":
             ops.advance_seed(dev)                 # new dropout masks this step (also under graph replay)

@@ -37,7 +37,8 @@ class ScaPlan:
     inv_count: torch.Tensor     # (bs, Nq) f32: 1 / max(1, #cameras seeing q)   (per batch item)
     row_map: torch.Tensor       # (bs*R,) int32: value map (b*ncam + cam) of every sampler row
     ref_cam: torch.Tensor       # (ncam, bs, Nq, D, 2) f32
-    num_pairs: int
+    num_pairs: int              # rows of the pair list (== its capacity for a device-built plan)
+    counters: Optional[torch.Tensor] = None   # device-built plans: int32 [pairs found, overflow flag]
 
     @staticmethod
     def build(bev_mask: torch.Tensor, reference_points_cam: torch.Tensor, bev_hw=None,
@@ -69,6 +70,28 @@ class ScaPlan:
                    + pair_cam[None, :]).reshape(-1).contiguous()
         return ScaPlan(pair_cam, pair_q, pair_of, inv_count.contiguous(), row_map,
                        reference_points_cam.float().contiguous(), r)
+
+
+    @staticmethod
+    def tile_order(bev_h: int, bev_w: int, device, tile: int = 8) -> torch.Tensor:
+        """(Nq,) int32: the BEV queries in tile x tile patches (row-major inside a patch) -- the order of
+        the queries inside each camera's pair list.  Depends on the BEV size only."""
+        qi = torch.arange(bev_h, device=device).view(bev_h, 1).expand(bev_h, bev_w).reshape(-1)
+        qj = torch.arange(bev_w, device=device).view(1, bev_w).expand(bev_h, bev_w).reshape(-1)
+        tiles_x = (bev_w + tile - 1) // tile
+        key = ((qi // tile) * tiles_x + qj // tile) * (tile * tile) + (qi % tile) * tile + qj % tile
+        return torch.argsort(key, stable=True).to(torch.int32).contiguous()
+
+    @staticmethod
+    def build_device(mask_u8: torch.Tensor, reference_points_cam: torch.Tensor, qorder, capacity: int) -> "ScaPlan":
+        """Same plan as ``build`` (same pairs, same order when ``qorder`` is the tile order), produced by
+        three small kernels with NO host synchronisation: the lists have a fixed ``capacity`` and unused
+        rows are marked -1, which every row-list kernel skips.  Capturable in a CUDA graph; replaying the
+        graph with a new lidar2img rebuilds the list for that frame.  ``counters`` = [pairs found, overflow]
+        stays on the device -- see BEVFormerEncoder.check_plan()."""
+        t = ops.sca_plan_build(mask_u8, qorder, capacity)
+        return ScaPlan(t["pair_cam"], t["pair_q"], t["pair_of"], t["inv_count"], t["row_map"],
+                       reference_points_cam.float().contiguous(), int(capacity), t["counters"])
 
 
 class MSDeformableAttention3D(nn.Module):

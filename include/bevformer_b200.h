@@ -153,6 +153,29 @@ BEVF_API int bevf_msda_set_backward_mode(int mode);
  * ---------------------------------------------------------------------------------------------- */
 
 /*
+ * In-view (camera, query) pair list of SpatialCrossAttention, built on the device without a host
+ * synchronisation (capturable in a CUDA graph; a new lidar2img every frame just changes the contents).
+ * replaces spatial_cross_attention.py:138-141 (per-camera nonzero() + max_len: two host syncs per layer)
+ * and the zero-padded re-batch at :144-153.
+ *   bev_mask   (ncam, B, Nq, D) uint8    the in-view mask bevf_point_sampling writes
+ *   qorder     (Nq,) int32 or NULL       order of the queries inside a camera's list (e.g. 8x8 BEV tiles)
+ *   pair_q, pair_cam (capacity,) int32   out; camera-major; entries >= num_pairs are -1
+ *   pair_of    (ncam, Nq) int32          out; row of (cam, q) or -1
+ *   row_map    (B*capacity,) int32       out; value map b*ncam+cam of sampler row b*capacity+r, -1 = unused
+ *   inv_count  (B, Nq) f32               out; 1 / max(1, #cameras seeing q in batch item b)  (:169-171)
+ *   counters   (2,) int32                out; [0] = number of pairs found, [1] = 1 if it exceeded capacity
+ *                                        (the pairs beyond capacity are dropped: the caller must check)
+ *   workspace  bevf_sca_plan_workspace_ints(ncam, Nq) int32
+ * The lists come from batch item 0's mask for every batch item, as in the reference (:139).  Every
+ * row-list entry point of this library skips rows whose pair_q / row_map entry is -1.
+ */
+BEVF_API int64_t bevf_sca_plan_workspace_ints(int ncam, int Nq);
+BEVF_API int bevf_sca_plan_build(const unsigned char *bev_mask, const int32_t *qorder, int32_t *pair_q,
+                                 int32_t *pair_cam, int32_t *pair_of, int32_t *row_map, float *inv_count,
+                                 int32_t *counters, int32_t *workspace, int B, int ncam, int Nq, int D,
+                                 int capacity, void *stream);
+
+/*
  * SCA sampling points.  replaces spatial_cross_attention.py:338-372 (view, softmax over L*P,
  * offset / (W_l, H_l), Z-anchor broadcast "point p uses anchor p mod D", add) for the in-view
  * (camera, query) pairs only.

@@ -498,7 +498,7 @@ class BEVFormerEncoder(nn.Module):
         bev_mask = None
         if plan is None:
             if dev.type != "cuda":
-                raise RuntimeError("BEVFormerEncoder: bevformer_b200 has no CPU path")
+                raise RuntimeError("BEVFormerEncoder: inputs must be CUDA tensors (bevformer_b200 has no CPU path)")
             plan = self.prepare(kwargs["img_metas"], bev_h, bev_w, dev, l2i_dev)
         ref_cam = plan.ref_cam
         if self.training and dev.type == "cuda":

@@ -422,15 +422,17 @@ class BEVFormerEncoder(nn.Module):
         if key not in cache:
             cache[key] = dict(qorder=ScaPlan.tile_order(bev_h, bev_w, device), capacity=None, last=None)
         ent = cache[key]
-        self._poll_plan(ent)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:                  # (event queries are not allowed while a capture is active)
+            self._poll_plan(ent)
         if ent["capacity"] is None:
-            if torch.cuda.is_current_stream_capturing():
+            if capturing:
                 raise RuntimeError("BEVFormerEncoder: run one eager forward (or prepare()) before capturing a "
                                    "CUDA graph, so that the SCA pair list can be sized")
             found = int((mask[:, 0] != 0).any(-1).sum())            # the one calibration sync
             ent["capacity"] = max(256, -(-int(found * 1.15 + 64) // 256) * 256)
         plan = ScaPlan.build_device(mask, ref_cam, ent["qorder"], ent["capacity"])
-        if not torch.cuda.is_current_stream_capturing():
+        if not capturing:
             # overflow is checked WITHOUT blocking: the counters travel to pinned memory behind an event
             # and are looked at by the next prepare() / check_plan()
             host = torch.empty(2, dtype=torch.int32, pin_memory=True)

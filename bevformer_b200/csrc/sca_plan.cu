@@ -13,6 +13,7 @@
 //   row_map (B * capacity,)          value map b * ncam + cam of sampler row b * capacity + r, -1 for unused rows
 //   pair_of (ncam, Nq)               row of (cam, q) or -1
 //   inv_count (B, Nq)                1 / max(1, #cameras that see q in batch item b)
+//   map_range (B * ncam, 2)          [first, end) sampler rows of every value map (rows of a map are contiguous)
 //   counters[0] = num_pairs (may exceed capacity), counters[1] = 1 if it did (pairs beyond capacity are dropped)
 // Stable stream compaction in three small launches: per-block hit counts, block offsets + local scan,
 // tail marking + inv_count.
@@ -31,8 +32,9 @@ __device__ __forceinline__ bool plan_hit(const unsigned char *mask, int cam, int
 
 __global__ void __launch_bounds__(kPlanThreads)
 sca_plan_count(const unsigned char *__restrict__ mask, const int *__restrict__ qorder,
-               int *__restrict__ block_counts, int B, int ncam, int Nq, int D) {
+               int *__restrict__ block_counts, int *__restrict__ cam_first, int B, int ncam, int Nq, int D) {
     const long long i = (long long)blockIdx.x * kPlanThreads + threadIdx.x;
+    if (blockIdx.x == 0 && (int)threadIdx.x < ncam) cam_first[threadIdx.x] = 0x7fffffff;
     bool hit = false;
     if (i < (long long)ncam * Nq) {
         const int cam = (int)(i / Nq), k = (int)(i % Nq);
@@ -44,9 +46,9 @@ sca_plan_count(const unsigned char *__restrict__ mask, const int *__restrict__ q
 
 __global__ void __launch_bounds__(kPlanThreads)
 sca_plan_fill(const unsigned char *__restrict__ mask, const int *__restrict__ qorder,
-              const int *__restrict__ block_counts, int *__restrict__ pair_q, int *__restrict__ pair_cam,
-              int *__restrict__ pair_of, int *__restrict__ row_map, int *__restrict__ counters, int B,
-              int ncam, int Nq, int D, int capacity) {
+              const int *__restrict__ block_counts, int *__restrict__ cam_first, int *__restrict__ pair_q,
+              int *__restrict__ pair_cam, int *__restrict__ pair_of, int *__restrict__ row_map,
+              int *__restrict__ counters, int B, int ncam, int Nq, int D, int capacity) {
     __shared__ int s_red[kPlanThreads / 32];
     __shared__ int s_base;
     // ---- offset of this block = sum of the counts of the blocks before it
@@ -91,6 +93,7 @@ sca_plan_fill(const unsigned char *__restrict__ mask, const int *__restrict__ qo
             for (int b = 0; b < B; ++b) row_map[(long long)b * capacity + pos] = b * ncam + cam;
         }
         pair_of[(long long)cam * Nq + q] = slot;
+        if (slot >= 0) atomicMin(cam_first + cam, slot);         // first row of this camera's list
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         int total = base;
@@ -103,9 +106,20 @@ sca_plan_fill(const unsigned char *__restrict__ mask, const int *__restrict__ qo
 __global__ void __launch_bounds__(kPlanThreads)
 sca_plan_finish(const unsigned char *__restrict__ mask, const int *__restrict__ counters,
                 int *__restrict__ pair_q, int *__restrict__ pair_cam, int *__restrict__ row_map,
-                float *__restrict__ inv_count, int B, int ncam, int Nq, int D, int capacity) {
+                float *__restrict__ inv_count, const int *__restrict__ cam_first,
+                int *__restrict__ map_range, int B, int ncam, int Nq, int D, int capacity) {
     const long long t = (long long)blockIdx.x * kPlanThreads + threadIdx.x;
     const int n = min(counters[0], capacity);
+    if (t < (long long)B * ncam) {                              // row range of value map b * ncam + cam
+        const int cam = (int)(t % ncam), b = (int)(t / ncam);
+        int first = n, end = n;                                 // a camera that sees nothing gets an empty range
+        for (int c = ncam - 1; c >= cam; --c) {
+            const int f = min(cam_first[c], n);
+            if (c > cam) end = min(end, f); else first = min(f, end);
+        }
+        map_range[2 * t] = b * capacity + first;
+        map_range[2 * t + 1] = b * capacity + end;
+    }
     if (t < capacity && t >= n) {                               // unused tail rows
         pair_q[t] = -1;
         pair_cam[t] = -1;
@@ -129,27 +143,31 @@ sca_plan_finish(const unsigned char *__restrict__ mask, const int *__restrict__ 
 using namespace bevf;
 
 extern "C" int64_t bevf_sca_plan_workspace_ints(int ncam, int Nq) {
-    return ((int64_t)ncam * Nq + kPlanThreads - 1) / kPlanThreads;
+    return ((int64_t)ncam * Nq + kPlanThreads - 1) / kPlanThreads + ncam;      // block counts + first row per camera
 }
 
 extern "C" int bevf_sca_plan_build(const unsigned char *bev_mask, const int32_t *qorder, int32_t *pair_q,
                                    int32_t *pair_cam, int32_t *pair_of, int32_t *row_map, float *inv_count,
-                                   int32_t *counters, int32_t *workspace, int B, int ncam, int Nq, int D,
-                                   int capacity, void *stream) {
+                                   int32_t *map_range, int32_t *counters, int32_t *workspace, int B, int ncam,
+                                   int Nq, int D, int capacity, void *stream) {
     const char *who = "bevf_sca_plan_build";
     if (B <= 0 || ncam <= 0 || Nq <= 0 || D <= 0 || capacity <= 0) return fail("%s: non-positive dimension", who);
-    if (!bev_mask || !pair_q || !pair_cam || !pair_of || !row_map || !inv_count || !counters || !workspace)
+    if (!bev_mask || !pair_q || !pair_cam || !pair_of || !row_map || !inv_count || !map_range || !counters ||
+        !workspace)
         return fail("%s: null pointer argument", who);
     cudaStream_t st = (cudaStream_t)stream;
     const long long seq = (long long)ncam * Nq;
     const unsigned blocks = (unsigned)((seq + kPlanThreads - 1) / kPlanThreads);
-    sca_plan_count<<<blocks, kPlanThreads, 0, st>>>(bev_mask, qorder, workspace, B, ncam, Nq, D);
+    int32_t *cam_first = workspace + blocks;
+    if (ncam > kPlanThreads) return fail("%s: at most 256 cameras", who);
+    sca_plan_count<<<blocks, kPlanThreads, 0, st>>>(bev_mask, qorder, workspace, cam_first, B, ncam, Nq, D);
     if (int e = check_launch(who)) return e;
-    sca_plan_fill<<<blocks, kPlanThreads, 0, st>>>(bev_mask, qorder, workspace, pair_q, pair_cam, pair_of,
-                                                  row_map, counters, B, ncam, Nq, D, capacity);
+    sca_plan_fill<<<blocks, kPlanThreads, 0, st>>>(bev_mask, qorder, workspace, cam_first, pair_q, pair_cam,
+                                                  pair_of, row_map, counters, B, ncam, Nq, D, capacity);
     if (int e = check_launch(who)) return e;
-    const long long fin = (long long)B * Nq > capacity ? (long long)B * Nq : capacity;
+    long long fin = (long long)B * Nq > capacity ? (long long)B * Nq : capacity;
+    if (fin < (long long)B * ncam) fin = (long long)B * ncam;
     sca_plan_finish<<<(unsigned)((fin + kPlanThreads - 1) / kPlanThreads), kPlanThreads, 0, st>>>(
-        bev_mask, counters, pair_q, pair_cam, row_map, inv_count, B, ncam, Nq, D, capacity);
+        bev_mask, counters, pair_q, pair_cam, row_map, inv_count, cam_first, map_range, B, ncam, Nq, D, capacity);
     return check_launch(who);
 }

@@ -222,6 +222,33 @@ def msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_m
     return out
 
 
+def msda_rows_forward_staged(value, spatial_shapes, level_start_index, level_hw_host, loc, attn, map_range,
+                             out_dtype=None):
+    """msda_rows_forward for row lists grouped by value map, coarse levels TMA-staged in shared memory
+    (bevf_msda_rows_forward_staged).  level_hw_host: [(h, w), ...] python ints; map_range (NB, 2) int32."""
+    import ctypes
+    for t, n in ((value, "value"), (loc, "sampling_loc"), (attn, "attn_weight"), (map_range, "map_range")):
+        _need_cuda(t, n)
+    if value.dtype not in _DT or loc.dtype != torch.float32 or attn.dtype != torch.float32:
+        raise RuntimeError("value must be float32/bfloat16, sampling_loc and attn_weight float32")
+    NB, S, M, D = value.shape
+    R, M2, L, P, _ = loc.shape
+    if M2 != M or tuple(attn.shape) != (R, M, L, P) or map_range.numel() != 2 * NB or len(level_hw_host) != L:
+        raise RuntimeError("value / sampling_loc / attn_weight / map_range / level shapes disagree")
+    ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
+    hw = (ctypes.c_int32 * (2 * L))(*[int(v) for hw_ in level_hw_host for v in hw_])
+    out_dtype = out_dtype or value.dtype
+    out = torch.empty((R, M * D), device=value.device, dtype=out_dtype)
+    lib = _lib.load()
+    with torch.cuda.device(value.device), _timed("msda_rows_forward", value.device, (R, L)):
+        st = lib.bevf_msda_rows_forward_staged(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                               ctypes.addressof(hw), loc.data_ptr(), attn.data_ptr(),
+                                               out.data_ptr(), _DT[out_dtype], map_range.data_ptr(),
+                                               NB, S, M, D, R, L, P, _stream_ptr(value))
+    _lib.check(st, lib)
+    return out
+
+
 def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
                        grad_value=None, group_order=None):
     """``group_order`` (R,) int32: optional permutation of the rows in which runs of 64 entries are
@@ -255,10 +282,16 @@ class SamplerRows(Function):
     """Sampler over a compact list of query rows (SCA's in-view (camera, query) pairs)."""
 
     @staticmethod
-    def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index, group_order=None):
+    def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index, group_order=None,
+                staged=None):
+        """``staged`` = (level_hw_host, map_range): use the TMA-staged forward (rows grouped by value map)."""
         if value.dtype == torch.float16:      # the reference widens half inputs (…function.py:93)
             value = value.float()
-        out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
+        if staged is not None and value.shape[-1] == 32 and os.environ.get("BEVF_MSDA_FWD", "staged") != "plain":
+            out = msda_rows_forward_staged(value, spatial_shapes, level_start_index, staged[0], loc, attn,
+                                           staged[1])
+        else:
+            out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         ctx.group_order = group_order
         return out
@@ -269,7 +302,7 @@ class SamplerRows(Function):
         value, loc, attn, row_map, ss, ls = ctx.saved_tensors
         gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(),
                                         group_order=ctx.group_order)
-        return gv.to(value.dtype), gl, ga, None, None, None, None
+        return gv.to(value.dtype), gl, ga, None, None, None, None, None
 
 
 def sca_prep_forward(raw, ref_cam, pair_q, pair_cam, level_hw, B, Nq, M, L, P):
@@ -544,13 +577,14 @@ def sca_plan_build(mask_u8, qorder, capacity):
     out = dict(pair_q=torch.empty(capacity, **i32), pair_cam=torch.empty(capacity, **i32),
                pair_of=torch.empty((ncam, Nq), **i32), row_map=torch.empty(B * capacity, **i32),
                inv_count=torch.empty((B, Nq), device=dev, dtype=torch.float32),
-               counters=torch.empty(2, **i32))
+               map_range=torch.empty((B * ncam, 2), **i32), counters=torch.empty(2, **i32))
     ws = torch.empty(int(lib.bevf_sca_plan_workspace_ints(ncam, Nq)), **i32)
     with torch.cuda.device(dev):
         st = lib.bevf_sca_plan_build(mask_u8.data_ptr(), _ptr(qorder), out["pair_q"].data_ptr(),
                                      out["pair_cam"].data_ptr(), out["pair_of"].data_ptr(),
                                      out["row_map"].data_ptr(), out["inv_count"].data_ptr(),
-                                     out["counters"].data_ptr(), ws.data_ptr(), B, ncam, Nq, D,
+                                     out["map_range"].data_ptr(), out["counters"].data_ptr(), ws.data_ptr(),
+                                     B, ncam, Nq, D,
                                      int(capacity), _stream_ptr(mask_u8))
     _lib.check(st, lib)
     return out

@@ -287,7 +287,7 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                 if fuse and isinstance(att, SpatialCrossAttention) and query_pos is None:
                     pre = att.attend(query, value if value is not None else key, reference_points_cam,
                                      kwargs.get("bev_mask"), spatial_shapes, level_start_index,
-                                     kwargs.get("sca_plan"))
+                                     kwargs.get("sca_plan"), kwargs.get("level_hw_host"))
                     query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1
@@ -473,6 +473,23 @@ class BEVFormerEncoder(nn.Module):
             return found
         return None
 
+    def _level_shapes_host(self, spatial_shapes):
+        """[(h, w), ...] as python ints, for the TMA tensor maps of the staged sampler.  Lists / CPU tensors
+        are read directly; a device tensor is read ONCE (one sync, never during a graph capture) and
+        remembered by its storage address -- safe to go stale, because the kernel re-checks the shapes
+        against the device tensor and falls back to the unstaged path on a mismatch."""
+        if not torch.is_tensor(spatial_shapes):
+            return [(int(h), int(w)) for h, w in spatial_shapes]
+        if not spatial_shapes.is_cuda:
+            return [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
+        cache = self.__dict__.setdefault("_ss_host_cache", {})
+        key = (spatial_shapes.data_ptr(), tuple(spatial_shapes.shape), str(spatial_shapes.device))
+        if key not in cache:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            cache[key] = [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
+        return cache[key]
+
     def _constants(self, bev_h, bev_w, bs, dev):
         """Small device tensors that never change for a BEV size (built once: creating a tensor from
         Python numbers is a pageable host copy, which a stream capture does not allow)."""
@@ -518,6 +535,7 @@ class BEVFormerEncoder(nn.Module):
             queue = None
             hybrid = torch.stack([ref_2d, ref_2d], 1).reshape(bs * 2, nq, 1, 2)
         hybrid = hybrid.contiguous()
+        hw_host = kwargs.pop("level_hw_host", None) or self._level_shapes_host(spatial_shapes)
         ss = torch.as_tensor(spatial_shapes).to(device=dev, dtype=torch.int64).contiguous()
         lsi = torch.as_tensor(level_start_index).to(device=dev, dtype=torch.int64).contiguous()
 
@@ -535,7 +553,8 @@ class BEVFormerEncoder(nn.Module):
             query = layer(query, key, value, *args, bev_pos=pos, ref_2d=hybrid, ref_3d=None,
                           bev_h=bev_h, bev_w=bev_w, spatial_shapes=ss, level_start_index=lsi,
                           reference_points_cam=ref_cam, bev_mask=bev_mask, prev_bev=queue,
-                          sca_plan=plan, tsa_spatial_shapes=tsa_ss, tsa_level_start_index=tsa_lsi,
+                          sca_plan=plan, level_hw_host=hw_host, tsa_spatial_shapes=tsa_ss,
+                          tsa_level_start_index=tsa_lsi,
                           **extra, **kwargs)
             if self.return_intermediate:
                 inter.append(query)

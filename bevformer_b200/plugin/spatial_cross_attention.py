@@ -39,6 +39,7 @@ class ScaPlan:
     ref_cam: torch.Tensor       # (ncam, bs, Nq, D, 2) f32
     num_pairs: int              # rows of the pair list (== its capacity for a device-built plan)
     counters: Optional[torch.Tensor] = None   # device-built plans: int32 [pairs found, overflow flag]
+    map_range: Optional[torch.Tensor] = None  # (bs*ncam, 2) int32: [first, end) sampler rows of every value map
 
     @staticmethod
     def build(bev_mask: torch.Tensor, reference_points_cam: torch.Tensor, bev_hw=None,
@@ -68,8 +69,13 @@ class ScaPlan:
         inv_count = 1.0 / seen.sum(0).clamp(min=1).to(torch.float32)
         row_map = (torch.arange(bs, device=bev_mask.device, dtype=torch.int32)[:, None] * ncam
                    + pair_cam[None, :]).reshape(-1).contiguous()
+        per_cam = torch.bincount(pair_cam.long(), minlength=ncam)
+        ends = per_cam.cumsum(0)
+        rng = torch.stack([ends - per_cam, ends], 1)                                  # (ncam, 2)
+        map_range = (rng[None] + (torch.arange(bs, device=rng.device) * r)[:, None, None]).reshape(-1, 2)
         return ScaPlan(pair_cam, pair_q, pair_of, inv_count.contiguous(), row_map,
-                       reference_points_cam.float().contiguous(), r)
+                       reference_points_cam.float().contiguous(), r, None,
+                       map_range.to(torch.int32).contiguous())
 
 
     @staticmethod
@@ -91,7 +97,7 @@ class ScaPlan:
         stays on the device -- see BEVFormerEncoder.check_plan()."""
         t = ops.sca_plan_build(mask_u8, qorder, capacity)
         return ScaPlan(t["pair_cam"], t["pair_q"], t["pair_of"], t["inv_count"], t["row_map"],
-                       reference_points_cam.float().contiguous(), int(capacity), t["counters"])
+                       reference_points_cam.float().contiguous(), int(capacity), t["counters"], t["map_range"])
 
 
 class MSDeformableAttention3D(nn.Module):
@@ -197,9 +203,11 @@ class SpatialCrossAttention(nn.Module):
         nn.init.zeros_(self.output_proj.bias)
 
     def attend(self, query, value, reference_points_cam, bev_mask, spatial_shapes,
-               level_start_index, plan: Optional[ScaPlan] = None):
+               level_start_index, plan: Optional[ScaPlan] = None, level_hw_host=None):
         """Everything up to and including output_proj, WITHOUT dropout / residual.
-        query (bs, Nq, C); value (num_cams, S, bs, C)."""
+        query (bs, Nq, C); value (num_cams, S, bs, C).  ``level_hw_host``: [(h, w), ...] python ints of
+        the pyramid, when the caller knows them without a device read: the sampler forward then stages
+        the coarse levels in shared memory through TMA."""
         da = self.deformable_attention
         bs, nq, c = query.shape
         ncam, s = value.shape[0], value.shape[1]
@@ -218,7 +226,10 @@ class SpatialCrossAttention(nn.Module):
         # value_proj over every camera's feature pyramid (:334), batch-major like the reference
         feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s, c)
         v = linear(feats, da.value_proj.weight, da.value_proj.bias).view(bs * ncam, s, m, -1)
-        out = ops.SamplerRows.apply(v, loc, attn, plan.row_map, ss, lsi)          # (bs*R, C)
+        staged = None
+        if level_hw_host is not None and plan.map_range is not None and len(level_hw_host) == l:
+            staged = (level_hw_host, plan.map_range)
+        out = ops.SamplerRows.apply(v, loc, attn, plan.row_map, ss, lsi, None, staged)   # (bs*R, C)
         slots = ops.ScaCombine.apply(out, plan.pair_of, plan.pair_q, plan.inv_count, bs, nq)
         return linear(slots, self.output_proj.weight, self.output_proj.bias)
 

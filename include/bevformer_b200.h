@@ -139,6 +139,24 @@ BEVF_API int bevf_msda_rows_backward_ordered(const void *value, int value_dtype,
                                              int R, int L, int P, void *stream);
 
 /*
+ * bevf_msda_rows_forward with the coarse pyramid levels staged in shared memory by TMA.
+ * For row lists whose rows are grouped by value map (the SCA pair list: camera-major): a CTA takes one
+ * (value map, head) and a share of that map's rows, loads every level that fits -- coarsest first, whole
+ * level of that head, one cp.async.bulk.tensor per level -- and gathers those levels from shared memory;
+ * finer levels keep the global path.  Same results as bevf_msda_rows_forward.
+ *   level_hw_host  (L, 2) int32 HOST copy of level_hw (the tensor maps are built on the host); a level
+ *                  whose host shape disagrees with the device-side level_hw / level_start is not staged
+ *   map_range      (B, 2) int32 DEVICE: [first, end) rows of every value map (bevf_sca_plan_build)
+ *   B = number of value maps; levels must be stored back to back (level_start[l] = sum of H*W before l,
+ *   the reference's own definition, transformer.py:178-180); head_dim 32.
+ */
+BEVF_API int bevf_msda_rows_forward_staged(const void *value, int value_dtype, const int64_t *level_hw,
+                                           const int64_t *level_start, const int32_t *level_hw_host,
+                                           const float *loc, const float *attn, void *out, int out_dtype,
+                                           const int32_t *map_range, int B, int S, int M, int D, int R,
+                                           int L, int P, void *stream);
+
+/*
  * Selects how bevf_msda_*backward* computes grad_value (process-wide; default 0, or the environment
  * variable BEVF_MSDA_BWD=split).  0: one kernel, one 16 B-vector L2 reduction per corner contribution.
  * 1: gather kernel + a splat kernel that merges the contributions of 64 neighbouring rows in registers
@@ -163,6 +181,8 @@ BEVF_API int bevf_msda_set_backward_mode(int mode);
  *   pair_of    (ncam, Nq) int32          out; row of (cam, q) or -1
  *   row_map    (B*capacity,) int32       out; value map b*ncam+cam of sampler row b*capacity+r, -1 = unused
  *   inv_count  (B, Nq) f32               out; 1 / max(1, #cameras seeing q in batch item b)  (:169-171)
+ *   map_range  (B*ncam, 2) int32         out; [first, end) sampler rows of value map b*ncam+cam (its rows are
+ *                                        contiguous) -- what bevf_msda_rows_forward_staged partitions by
  *   counters   (2,) int32                out; [0] = number of pairs found, [1] = 1 if it exceeded capacity
  *                                        (the pairs beyond capacity are dropped: the caller must check)
  *   workspace  bevf_sca_plan_workspace_ints(ncam, Nq) int32
@@ -172,8 +192,8 @@ BEVF_API int bevf_msda_set_backward_mode(int mode);
 BEVF_API int64_t bevf_sca_plan_workspace_ints(int ncam, int Nq);
 BEVF_API int bevf_sca_plan_build(const unsigned char *bev_mask, const int32_t *qorder, int32_t *pair_q,
                                  int32_t *pair_cam, int32_t *pair_of, int32_t *row_map, float *inv_count,
-                                 int32_t *counters, int32_t *workspace, int B, int ncam, int Nq, int D,
-                                 int capacity, void *stream);
+                                 int32_t *map_range, int32_t *counters, int32_t *workspace, int B, int ncam,
+                                 int Nq, int D, int capacity, void *stream);
 
 /*
  * SCA sampling points.  replaces spatial_cross_attention.py:338-372 (view, softmax over L*P,

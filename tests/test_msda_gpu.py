@@ -221,3 +221,40 @@ def _robust(got, want, tol, max_outlier_frac=1e-4):
     frac = ((got - want).abs() > tol * scale).double().mean().item()
     l2 = ((got - want).norm() / max(want.norm().item(), 1e-12)).item()
     return frac <= max_outlier_frac and l2 < 5 * tol, (l2, frac)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bs", [1, 2])
+def test_staged_forward_equals_plain(dtype, bs):
+    """bevf_msda_rows_forward_staged (coarse levels TMA-staged in shared memory) against the plain
+    row-list forward on the real SCA geometry: same inputs, same arithmetic -> bit-identical rows; a
+    camera with no rows, a wrong host shape (fallback to the global path) and bs > 1 included."""
+    from tools.bench_msda import rig_sca_inputs
+    from bevformer_b200.plugin import ScaPlan
+    v, ss, lsi, loc, attn, row_map = rig_sca_inputs(DEV)
+    w = syn.WORKLOADS["base"]
+    R = loc.shape[0]
+    per_cam = torch.bincount(row_map.long(), minlength=6)
+    ends = per_cam.cumsum(0)
+    rng = torch.stack([ends - per_cam, ends], 1)
+    if bs == 2:                      # second batch item: rows b*R + r on maps 6..11
+        v = torch.cat([v, v.flip(0)], 0)
+        loc = torch.cat([loc, loc.flip(0)], 0)
+        attn = torch.cat([attn, attn.flip(0)], 0)
+        # rows of item 1 are the flipped list: camera order reversed -> ranges must follow the row order
+        row_map = torch.cat([row_map, 6 + row_map.flip(0)], 0)
+        per2 = per_cam.flip(0)
+        e2 = per2.cumsum(0)
+        r2 = torch.stack([e2 - per2, e2], 1).flip(0) + R
+        rng = torch.cat([rng, r2], 0)
+    map_range = rng.to(torch.int32).contiguous()
+    vd = v.to(dtype)
+    plain = ops.msda_rows_forward(vd, ss, lsi, loc, attn, row_map.contiguous())
+    staged = ops.msda_rows_forward_staged(vd, ss, lsi, list(w.levels), loc, attn, map_range)
+    torch.cuda.synchronize()
+    assert torch.equal(plain, staged)
+    # host shapes that do not match the device tensor: every level falls back to the global path
+    wrong = [(h, ww) for h, ww in w.levels]
+    wrong[-1], wrong[-2] = (25, 15), (50, 29)
+    staged2 = ops.msda_rows_forward_staged(vd, ss, lsi, wrong, loc, attn, map_range)
+    assert torch.equal(plain, staged2)

@@ -44,6 +44,10 @@ def test_device_plan_equals_host_plan(workload, bs, ordered):
     assert bool((plan.pair_q[n:] == -1).all()) and bool((plan.pair_cam[n:] == -1).all())
     assert torch.equal(plan.pair_of, host.pair_of)
     assert torch.equal(plan.inv_count, host.inv_count)
+    # row ranges per value map: host plan rows are b*n + r, device plan rows b*cap + r
+    hr = host.map_range.view(bs, -1, 2) - (torch.arange(bs, device=DEV) * n).view(bs, 1, 1).int()
+    dr = plan.map_range.view(bs, -1, 2) - (torch.arange(bs, device=DEV) * cap).view(bs, 1, 1).int()
+    assert torch.equal(hr, dr)
     rm = plan.row_map.view(bs, cap)
     assert torch.equal(rm[:, :n].reshape(-1), host.row_map) and bool((rm[:, n:] == -1).all())
 

@@ -145,6 +145,7 @@ template <> struct Vec<bf16> {
 template <int LANES> struct GroupMask;
 template <> struct GroupMask<4> { static constexpr unsigned kBits = 0x11111111u; };
 template <> struct GroupMask<8> { static constexpr unsigned kBits = 0x01010101u; };
+template <> struct GroupMask<16> { static constexpr unsigned kBits = 0x00010001u; };
 
 // level of flat sample index s (= s / P) without an integer division: magic = ceil(2^16 / P),
 // exact while s * P < 2^16 (checked on the host: L * P * P < 65536).

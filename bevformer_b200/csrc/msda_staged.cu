@@ -56,21 +56,35 @@ struct StagedTab {
     int srow[kMaxLevels];         // bytes between image rows in the staged copy
 };
 
+// Lane mapping (bf16): 8 lanes per (row, head) -- lanes 0-3 own the LEFT corner column (x0), lanes 4-7 the
+// RIGHT one (x0 + 1), 16 B (8 channels) each; a warp covers 4 rows.  In the staged copy of a level the
+// pixels of one head are dense, so the left and right corner of a sample are ADJACENT 64 B rows: the 8
+// lanes of a group read one contiguous 128 B span per image row -- a conflict-free shared-memory phase,
+// two ld.shared.v4 per sample instead of four 64 B gathers.  The two column sums meet in one shuffle per
+// accumulator at the end of the row.  Unstaged (fine) levels use the same mapping on the global path.
+// Work distribution: persistent CTAs (one per SM); the rows of every value map are cut into units of
+// kUnitRows rows x one head, listed (map, head, chunk)-major, and every CTA takes an equal contiguous
+// share of the list, re-staging whenever the (map, head) changes (117 KB from L2: ~1 us per 40 us unit).
+constexpr int kUnitRows = 512;
+
 template <typename T, typename TO>
 __global__ void __launch_bounds__(kStagedThreads, 1)
 msda_fwd_staged_d32(const __grid_constant__ StagedMaps maps, const StagedInfo info,
                     const T *__restrict__ value, const int64_t *__restrict__ level_hw,
                     const int64_t *__restrict__ level_start, const float *__restrict__ loc,
                     const float *__restrict__ attn, TO *__restrict__ out,
-                    const int *__restrict__ map_range, int S, int M, int L, int P, int magic) {
-    constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
+                    const int *__restrict__ map_range, int NB, int S, int M, int L, int P, int magic) {
+    constexpr int VEC = Vec<T>::N;                 // channels per lane (16 B)
+    constexpr int QL = 32 / VEC;                   // lanes per 32-channel row: 4 (bf16) / 8 (fp32)
+    constexpr int LANES = 2 * QL;                  // lanes per (row, head): left + right column
+    constexpr int G = 32 / LANES;                  // rows per warp: 4 (bf16) / 2 (fp32)
     constexpr bool kHalf = (VEC == 8);
     constexpr int kRowBytes = 32 * (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char stage[];
     __shared__ StagedTab tab;
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_ok[kMaxStaged];
 
-    const int b = blockIdx.z, m = blockIdx.y;
     const int pix = M * 32;
     if ((int)threadIdx.x < L) {
         const int l = threadIdx.x;
@@ -88,113 +102,132 @@ msda_fwd_staged_d32(const __grid_constant__ StagedMaps maps, const StagedInfo in
     __syncthreads();
     if (threadIdx.x == 0) {
         // the host's idea of the staged levels must match the device's spatial_shapes / level_start
-        unsigned total = 0;
         long long start = 0;
-        bool okv[kMaxStaged];
-        for (int i = 0; i < info.nstaged; ++i) okv[i] = false;
-        for (int l = 0, i = 0; l < L; ++l) {
-            for (i = 0; i < info.nstaged; ++i)
+        for (int i = 0; i < kMaxStaged; ++i) s_ok[i] = 0;
+        for (int l = 0; l < L; ++l) {
+            for (int i = 0; i < info.nstaged; ++i)
                 if (info.level[i] == l && info.h[i] == tab.h[l] && info.w[i] == tab.w[l] &&
                     tab.lofs[l] == start * pix) {
-                    okv[i] = true;
-                    total += (unsigned)info.bytes[i];
+                    s_ok[i] = 1;
+                    tab.sbase[l] = (int)s_u32(stage + info.smem_off[i]);
+                    tab.srow[l] = info.w[i] * kRowBytes;
                 }
             start += (long long)tab.h[l] * tab.w[l];
         }
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&bar)), "r"(total) : "memory");
-        for (int i = 0; i < info.nstaged; ++i) {
-            if (!okv[i]) continue;
-            const int l = info.level[i];
-            tab.sbase[l] = (int)s_u32(stage + info.smem_off[i]);
-            tab.srow[l] = info.w[i] * kRowBytes;
-            tma_load_5d(s_u32(stage + info.smem_off[i]), &maps.m[i], s_u32(&bar), 0, m, 0, 0, b);
-        }
     }
-    // this CTA's share of the map's rows (pairs), in multiples of G
-    const int ps = __ldg(map_range + 2 * b), pe = __ldg(map_range + 2 * b + 1);
-    const int n = pe - ps;
-    int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
-    per = (per + G - 1) / G * G;
-    const int r0 = ps + (int)blockIdx.x * per;
-    const int r1 = min(pe, r0 + per);
-    __syncthreads();                                   // tab.sbase / srow visible
-    {   // wait for the staged levels (phase 0)
-        asm volatile(
-            "{\n.reg .pred p;\nWAITL:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra DONEL;\nbra WAITL;\nDONEL:\n}\n"
-            ::"r"(s_u32(&bar)) : "memory");
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % LANES, grp = lane / LANES;
-    const int LP = L * P;
-    const T *vmap = value + ((long long)b * S * M + m) * 32 + sub * VEC;
+    __syncthreads();
 
-    for (int base = r0 + warp * G; base < r1; base += (kStagedThreads / 32) * G) {
-        int pair = base + grp;
-        const bool live = pair < r1;
-        if (!live) pair = r1 - 1;
-        const long long row = (long long)pair * M + m;
-        const float2 *locp = reinterpret_cast<const float2 *>(loc) + row * LP;
-        const float *attp = attn + row * LP;
-        float acc[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-        for (int s0 = 0; s0 < LP; s0 += LANES) {
-            const int sm = s0 + sub;
-            int enc = 0;                          // (clamped top-left pixel index << 2) | dx | dy << 1
-            float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
-            bool valid = false;
-            if (sm < LP && live) {
-                const int l = level_of(sm, magic);
-                const float2 xy = __ldg(locp + sm);
-                const float a = __ldg(attp + sm);
-                const Corner c = make_corner(xy.x, xy.y, tab.h[l], tab.w[l]);
-                enc = (c.pidx << 2) | c.dx | (c.dy << 1);
-                valid = c.valid;
-                w00 = c.w00 * a; w01 = c.w01 * a; w10 = c.w10 * a; w11 = c.w11 * a;
-            }
-            uint32_t wa = 0, wb = 0;
-            if constexpr (kHalf) { wa = pack_bf16x2(w00, w01); wb = pack_bf16x2(w10, w11); }
-            const unsigned vm = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-            for (int j = 0; j < LANES; ++j) {
-                if (s0 + j >= LP) break;
-                if (!(vm & (GroupMask<LANES>::kBits << j))) continue;
-                const int src = grp * LANES + j;
-                const unsigned e = (unsigned)__shfl_sync(0xffffffffu, enc, src);
-                const int l = level_of(s0 + j, magic);
-                const unsigned p00 = e >> 2;
-                Vec<T> v00, v01, v10, v11;
-                const int sb = tab.sbase[l];                 // warp-uniform
-                if (sb != 0) {
-                    const uint32_t a00 = (uint32_t)sb + p00 * kRowBytes + sub * 16;
-                    const uint32_t a01 = a00 + ((e & 1u) ? (uint32_t)kRowBytes : 0u);
-                    const uint32_t oy = (e & 2u) ? (uint32_t)tab.srow[l] : 0u;
-                    v00.v = vec_bits<T>(lds128(a00)); v01.v = vec_bits<T>(lds128(a01));
-                    v10.v = vec_bits<T>(lds128(a00 + oy)); v11.v = vec_bits<T>(lds128(a01 + oy));
-                } else {
-                    const T *vl = vmap + tab.lofs[l];
-                    const unsigned o00 = p00 * (unsigned)pix;
-                    const unsigned o01 = o00 + ((e & 1u) ? (unsigned)pix : 0u);
-                    const unsigned oy = (e & 2u) ? (unsigned)tab.rs[l] : 0u;
-                    v00.load(vl + o00); v01.load(vl + o01); v10.load(vl + (o00 + oy)); v11.load(vl + (o01 + oy));
-                }
-                if constexpr (kHalf) {
-                    const uint32_t qa = __shfl_sync(0xffffffffu, wa, src);
-                    const uint32_t qb = __shfl_sync(0xffffffffu, wb, src);
-                    unsigned short h00, h01, h10, h11;
-                    split16(qa, h00, h01);
-                    split16(qb, h10, h11);
-                    v00.axpy_h(h00, acc); v01.axpy_h(h01, acc); v10.axpy_h(h10, acc); v11.axpy_h(h11, acc);
-                } else {
-                    const float q00 = __shfl_sync(0xffffffffu, w00, src);
-                    const float q01 = __shfl_sync(0xffffffffu, w01, src);
-                    const float q10 = __shfl_sync(0xffffffffu, w10, src);
-                    const float q11 = __shfl_sync(0xffffffffu, w11, src);
-                    v00.axpy(q00, acc); v01.axpy(q01, acc); v10.axpy(q10, acc); v11.axpy(q11, acc);
-                }
-            }
+    // ---- this CTA's share of the unit list
+    int total = 0;
+    for (int bb = 0; bb < NB; ++bb) {
+        const int n = __ldg(map_range + 2 * bb + 1) - __ldg(map_range + 2 * bb);
+        total += ((n + kUnitRows - 1) / kUnitRows) * M;
+    }
+    const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int u0 = (int)blockIdx.x * per_cta, u1 = min(total, u0 + per_cta);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / LANES, gl = lane % LANES;     // row group, lane inside it
+    const int half = gl / QL, sub = gl % QL;             // corner column (0 left / 1 right), 16 B slice
+    const int LP = L * P;
+    int cur_b = -1, cur_m = -1;
+    uint32_t phase = 0;
+
+    for (int u = u0; u < u1; ++u) {
+        // decode unit -> (map b, head m, chunk)
+        int b = 0, rem = u, cnt = 0, ps = 0, pe = 0;
+        for (; b < NB; ++b) {
+            ps = __ldg(map_range + 2 * b); pe = __ldg(map_range + 2 * b + 1);
+            cnt = (pe - ps + kUnitRows - 1) / kUnitRows;
+            if (rem < cnt * M) break;
+            rem -= cnt * M;
         }
-        if (live) store_vec<TO, VEC>(out + row * 32 + sub * VEC, acc);
+        const int m = rem / cnt, chunk = rem - m * cnt;
+        const int r0 = ps + chunk * kUnitRows, r1 = min(pe, r0 + kUnitRows);
+        if (b != cur_b || m != cur_m) {                   // (re-)stage the coarse levels of (b, m)
+            __syncthreads();                              // every warp is done with the previous copy
+            if (threadIdx.x == 0) {
+                unsigned bytes = 0;
+                for (int i = 0; i < info.nstaged; ++i) if (s_ok[i]) bytes += (unsigned)info.bytes[i];
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&bar)), "r"(bytes) : "memory");
+                for (int i = 0; i < info.nstaged; ++i)
+                    if (s_ok[i]) tma_load_5d(s_u32(stage + info.smem_off[i]), &maps.m[i], s_u32(&bar), 0, m, 0, 0, b);
+            }
+            asm volatile(
+                "{\n.reg .pred p;\nWAITL:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONEL;\nbra WAITL;\nDONEL:\n}\n"
+                ::"r"(s_u32(&bar)), "r"(phase) : "memory");
+            phase ^= 1u;
+            cur_b = b; cur_m = m;
+        }
+        const T *vmap = value + ((long long)b * S * M + m) * 32 + sub * VEC;
+
+        for (int base = r0 + warp * G; base < r1; base += (kStagedThreads / 32) * G) {
+            int pair = base + grp;
+            const bool live = pair < r1;
+            if (!live) pair = r1 - 1;
+            const long long row = (long long)pair * M + m;
+            const float2 *locp = reinterpret_cast<const float2 *>(loc) + row * LP;
+            const float *attp = attn + row * LP;
+            float acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+            for (int s0 = 0; s0 < LP; s0 += LANES) {
+                // ---- produce: lane gl of the group prepares sample s0 + gl
+                const int sm = s0 + gl;
+                int enc = 0;                      // (clamped top-left pixel index << 2) | dx | dy << 1
+                float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+                bool valid = false;
+                if (sm < LP && live) {
+                    const int l = level_of(sm, magic);
+                    const float2 xy = __ldg(locp + sm);
+                    const float a = __ldg(attp + sm);
+                    const Corner c = make_corner(xy.x, xy.y, tab.h[l], tab.w[l]);
+                    enc = (c.pidx << 2) | c.dx | (c.dy << 1);
+                    valid = c.valid;
+                    w00 = c.w00 * a; w01 = c.w01 * a; w10 = c.w10 * a; w11 = c.w11 * a;
+                }
+                uint32_t wa = 0, wb = 0;
+                if constexpr (kHalf) { wa = pack_bf16x2(w00, w01); wb = pack_bf16x2(w10, w11); }
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                // ---- consume: the LANES samples of this round, one after the other
+#pragma unroll
+                for (int j = 0; j < LANES; ++j) {
+                    if (s0 + j >= LP) break;
+                    if (!(vm & (GroupMask<LANES>::kBits << j))) continue;
+                    const int src = grp * LANES + j;
+                    const unsigned e = (unsigned)__shfl_sync(0xffffffffu, enc, src);
+                    const int l = level_of(s0 + j, magic);
+                    const unsigned pcol = (e >> 2) + ((half && (e & 1u)) ? 1u : 0u);   // pixel of MY corner column, top row
+                    Vec<T> vt, vb;                                                   // top / bottom corner of my column
+                    const int sb = tab.sbase[l];                                     // warp-uniform
+                    if (sb != 0) {
+                        const uint32_t at = (uint32_t)sb + pcol * kRowBytes + sub * 16;
+                        vt.v = vec_bits<T>(lds128(at));
+                        vb.v = vec_bits<T>(lds128(at + ((e & 2u) ? (uint32_t)tab.srow[l] : 0u)));
+                    } else {
+                        const T *vl = vmap + tab.lofs[l];
+                        const unsigned ot = pcol * (unsigned)pix;
+                        vt.load(vl + ot);
+                        vb.load(vl + (ot + ((e & 2u) ? (unsigned)tab.rs[l] : 0u)));
+                    }
+                    if constexpr (kHalf) {
+                        const uint32_t qa = __shfl_sync(0xffffffffu, wa, src);       // {w00 | w01 << 16}
+                        const uint32_t qb = __shfl_sync(0xffffffffu, wb, src);       // {w10 | w11 << 16}
+                        const unsigned short ht = (unsigned short)(half ? (qa >> 16) : (qa & 0xffffu));
+                        const unsigned short hb = (unsigned short)(half ? (qb >> 16) : (qb & 0xffffu));
+                        vt.axpy_h(ht, acc); vb.axpy_h(hb, acc);
+                    } else {
+                        const float qt = __shfl_sync(0xffffffffu, half ? w01 : w00, src);
+                        const float qb = __shfl_sync(0xffffffffu, half ? w11 : w10, src);
+                        vt.axpy(qt, acc); vb.axpy(qb, acc);
+                    }
+                }
+            }
+            // left + right corner columns
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], QL);
+            if (live && half == 0) store_vec<TO, VEC>(out + row * 32 + sub * VEC, acc);
+        }
     }
 }
 
@@ -266,9 +299,8 @@ static int launch_staged(const char *who, const void *value, const int64_t *hw_d
         }
         attr_done = true;
     }
-    dim3 grid((unsigned)chunks, (unsigned)M, (unsigned)NB);
-    msda_fwd_staged_d32<T, TO><<<grid, kStagedThreads, (size_t)used, st>>>(
-        maps, info, (const T *)value, hw_dev, ls_dev, loc, attn, (TO *)out, map_range, S, M, L, P,
+    msda_fwd_staged_d32<T, TO><<<(unsigned)chunks, kStagedThreads, (size_t)used, st>>>(
+        maps, info, (const T *)value, hw_dev, ls_dev, loc, attn, (TO *)out, map_range, NB, S, M, L, P,
         (65536 + P - 1) / P);
     return check_launch(who);
 }
@@ -299,8 +331,7 @@ extern "C" int bevf_msda_rows_forward_staged(const void *value, int value_dtype,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    int chunks = sms / (B * M);                    // one CTA per SM, maps x heads x chunks ~ number of SMs
-    if (chunks < 1) chunks = 1;
+    const int chunks = sms;                        // persistent: one CTA per SM
     const bool vb = value_dtype == BEVF_DTYPE_BF16, ob = out_dtype == BEVF_DTYPE_BF16;
     int e;
     if (vb && ob) e = launch_staged<bf16, bf16>(who, value, level_hw, level_start, level_hw_host, loc, attn, out, map_range, B, S, M, L, P, chunks, st);

@@ -287,7 +287,8 @@ class SamplerRows(Function):
         """``staged`` = (level_hw_host, map_range): use the TMA-staged forward (rows grouped by value map)."""
         if value.dtype == torch.float16:      # the reference widens half inputs (…function.py:93)
             value = value.float()
-        if staged is not None and value.shape[-1] == 32 and os.environ.get("BEVF_MSDA_FWD", "staged") != "plain":
+        # measured slower than the plain kernel on B200 (profiles/README.md, r2g): opt-in for A/B runs
+        if staged is not None and value.shape[-1] == 32 and os.environ.get("BEVF_MSDA_FWD", "plain") == "staged":
             out = msda_rows_forward_staged(value, spatial_shapes, level_start_index, staged[0], loc, attn,
                                            staged[1])
         else:

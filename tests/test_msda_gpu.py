@@ -227,8 +227,9 @@ def _robust(got, want, tol, max_outlier_frac=1e-4):
 @pytest.mark.parametrize("bs", [1, 2])
 def test_staged_forward_equals_plain(dtype, bs):
     """bevf_msda_rows_forward_staged (coarse levels TMA-staged in shared memory) against the plain
-    row-list forward on the real SCA geometry: same inputs, same arithmetic -> bit-identical rows; a
-    camera with no rows, a wrong host shape (fallback to the global path) and bs > 1 included."""
+    row-list forward on the real SCA geometry: same inputs, same products, the two corner columns summed
+    in a different order -> agreement to fp32 rounding (one bf16 ulp after the output rounding); a wrong
+    host shape (fallback to the global path) and bs > 1 included."""
     from tools.bench_msda import rig_sca_inputs
     from bevformer_b200.plugin import ScaPlan
     v, ss, lsi, loc, attn, row_map = rig_sca_inputs(DEV)
@@ -252,9 +253,10 @@ def test_staged_forward_equals_plain(dtype, bs):
     plain = ops.msda_rows_forward(vd, ss, lsi, loc, attn, row_map.contiguous())
     staged = ops.msda_rows_forward_staged(vd, ss, lsi, list(w.levels), loc, attn, map_range)
     torch.cuda.synchronize()
-    assert torch.equal(plain, staged)
+    tol = 1e-5 if dtype == torch.float32 else 8e-3      # bf16: at most one ulp of the rounded output
+    assert rel_err(staged.float(), plain.float()) < tol
     # host shapes that do not match the device tensor: every level falls back to the global path
     wrong = [(h, ww) for h, ww in w.levels]
     wrong[-1], wrong[-2] = (25, 15), (50, 29)
     staged2 = ops.msda_rows_forward_staged(vd, ss, lsi, wrong, loc, attn, map_range)
-    assert torch.equal(plain, staged2)
+    assert rel_err(staged2.float(), plain.float()) < tol

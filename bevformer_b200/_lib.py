@@ -55,6 +55,7 @@ SIGNATURES = {
                             + [c_int, c_int64, c_int, c_int, c_int, c_void_p]),
     "bevf_flatten_feats": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     "bevf_linear_dgrad": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_void_p]),
+    "bevf_linear_dgrad_acc": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_void_p]),
     "bevf_linear_wgrad": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_void_p]),
     "bevf_linear_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "bevf_linear_wgrad_out": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_int64, c_int64, c_int, c_int,

@@ -311,6 +311,8 @@ struct GemmWsParams {
     int out_f32;
     int b_mn;              // 0: B = weight (N, K) row-major, K-major tiles (Y = X W^T)
                            // 1: B = (K, N) row-major, MN-major tiles (Y = X B; dX = dY W without W^T)
+    const bf16 *addend;    // optional (M, N) bf16 added in the epilogue (bf16 output only): the running sum
+                           // of the input gradients of layers that share an input (dX_total = dX_prev + dY W)
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t chunk_bytes);
@@ -469,13 +471,20 @@ gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 4; ++i) tmem_ld16(taddr + (uint32_t)(c0 + 16 * i), r[i]);
                         tmem_ld_wait();
+                        const int grow = row0 + lane;                 // this thread's output row
+                        const bf16 *arow = (p.addend && grow < p.M)
+                                               ? p.addend + (size_t)grow * p.N + tn * p.BN + c0 : nullptr;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {                 // eight 16 B chunks = 8 columns each
                             float v[8];
+                            uint4 av = make_uint4(0, 0, 0, 0);
+                            if (arow) av = *reinterpret_cast<const uint4 *>(arow + 8 * i);
+                            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int c = 8 * i + j;
                                 float t = __uint_as_float(r[c >> 4][c & 15]) + s_bias[c0 + c];
+                                t += (j & 1) ? bf16_hi(aw[j >> 1]) : bf16_lo(aw[j >> 1]);
                                 v[j] = p.relu ? fmaxf(t, 0.f) : t;
                             }
                             uint4 o;
@@ -1008,7 +1017,8 @@ static int pick_bn(int N) {
 // weight-stationary launch shared by the forward projection (b_mn = 0, B = W (N, K)) and the input
 // gradient (b_mn = 1, B = W (K_red, N_out) read in place)
 static int launch_ws(const char *who, const void *x, const void *b, const void *bias, int bias_dtype, void *y,
-                     bool f32, int64_t M, int N, int K, int bn_ws, int relu, int b_mn, void *stream) {
+                     bool f32, int64_t M, int N, int K, int bn_ws, int relu, int b_mn, void *stream,
+                     const void *addend = nullptr) {
     CUtensorMap map_a, map_b, map_y;
     if (int e = make_map_2d(&map_a, x, (uint64_t)M, (uint64_t)K, kBM))
         return fail("%s: cuTensorMapEncodeTiled(A) failed (%lld)", who, e);
@@ -1020,6 +1030,7 @@ static int launch_ws(const char *who, const void *x, const void *b, const void *
     GemmWsParams q;
     q.M = (int)M; q.N = N; q.K = K; q.BN = bn_ws; q.relu = relu; q.bias = bias;
     q.bias_bf16 = bias_dtype == BEVF_DTYPE_BF16; q.out_f32 = f32 ? 1 : 0; q.b_mn = b_mn;
+    q.addend = f32 ? nullptr : reinterpret_cast<const bf16 *>(addend);
     const int b_bytes = ((bn_ws * K * 2) + 1023) & ~1023;
     int stages = (227 * 1024 - 1024 - b_bytes - 32 * 1024 - 1024 - 256) / (kBM * 128);
     if (stages > 6) stages = 6;
@@ -1043,8 +1054,21 @@ static int launch_ws(const char *who, const void *x, const void *b, const void *
 
 using namespace bevf;
 
+static int linear_dgrad_impl(const char *who, const void *dy, const void *w, const void *addend, void *dx, int64_t M,
+                             int N, int K, void *stream);
+
 extern "C" int bevf_linear_dgrad(const void *dy, const void *w, void *dx, int64_t M, int N, int K, void *stream) {
-    const char *who = "bevf_linear_dgrad";
+    return linear_dgrad_impl("bevf_linear_dgrad", dy, w, nullptr, dx, M, N, K, stream);
+}
+
+extern "C" int bevf_linear_dgrad_acc(const void *dy, const void *w, const void *addend, void *dx, int64_t M, int N,
+                                     int K, void *stream) {
+    if (addend && !aligned16(addend)) return fail("%s: addend must be 16-byte aligned", "bevf_linear_dgrad_acc");
+    return linear_dgrad_impl("bevf_linear_dgrad_acc", dy, w, addend, dx, M, N, K, stream);
+}
+
+static int linear_dgrad_impl(const char *who, const void *dy, const void *w, const void *addend, void *dx, int64_t M,
+                             int N, int K, void *stream) {
     if (M < 0 || N <= 0 || K <= 0) return fail("%s: bad dimension", who);
     if (M == 0) return 0;
     if (!dy || !w || !dx) return fail("%s: null pointer argument", who);
@@ -1054,7 +1078,7 @@ extern "C" int bevf_linear_dgrad(const void *dy, const void *w, void *dx, int64_
     // output columns = K of the weight, reduction = its N rows
     const int bn = pick_bn_ws(K, N, 64);
     if (bn == 0) return fail("%s: no 64-column tile of the weight fits shared memory", who);
-    return launch_ws(who, dy, w, nullptr, BEVF_DTYPE_F32, dx, false, M, K, N, bn, 0, 1, stream);
+    return launch_ws(who, dy, w, nullptr, BEVF_DTYPE_F32, dx, false, M, K, N, bn, 0, 1, stream, addend);
 }
 
 extern "C" int bevf_linear_forward(const void *x, const void *w, const void *bias, int bias_dtype,

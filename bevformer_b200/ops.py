@@ -635,22 +635,30 @@ def linear_tc(x, weight, bias=None, residual=None, relu=False, out_dtype=None):
     return y
 
 
-def linear_dgrad_tc(dy, weight):
-    """dx = dy @ weight on the tcgen05 GEMM, the weight (N, K) read in place (no transposed copy).
-    dy (M, N) bf16 -> (M, K) bf16.  N or K not a multiple of 64: falls back to the transposed-copy form."""
+def linear_dgrad_tc(dy, weight, addend=None):
+    """dx = dy @ weight (+ addend) on the tcgen05 GEMM, the weight (N, K) read in place (no transposed
+    copy).  dy (M, N) bf16 -> (M, K) bf16; ``addend`` (M, K) bf16 is summed in the epilogue.  N or K not
+    a multiple of 64: falls back to the transposed-copy form."""
     _need_cuda(dy, "dy")
     if dy.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or dy.shape[-1] != weight.shape[0]:
         raise RuntimeError("linear_dgrad_tc: dy (M,N) and weight (N,K) must be bfloat16")
     N, K = weight.shape
     if N % 64 or K % 64 or os.environ.get("BEVF_DGRAD", "mn") == "copy":
-        return linear_tc(dy, weight.t().contiguous())
+        dx = linear_tc(dy, weight.t().contiguous())
+        return dx if addend is None else dx + addend.view(dx.shape)
     dy = dy.contiguous()
     w = weight.contiguous()
     M = dy.numel() // N
     dx = torch.empty(dy.shape[:-1] + (K,), device=dy.device, dtype=torch.bfloat16)
     lib = _lib.load()
     with torch.cuda.device(dy.device):
-        st = lib.bevf_linear_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, N, K, _stream_ptr(dy))
+        if addend is None:
+            st = lib.bevf_linear_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, N, K, _stream_ptr(dy))
+        else:
+            if addend.dtype != torch.bfloat16 or addend.numel() != M * K or not addend.is_contiguous():
+                raise RuntimeError("linear_dgrad_tc: addend must be a contiguous bf16 (M, K) tensor")
+            st = lib.bevf_linear_dgrad_acc(dy.data_ptr(), w.data_ptr(), addend.data_ptr(), dx.data_ptr(), M, N, K,
+                                           _stream_ptr(dy))
     _lib.check(st, lib)
     return dx
 

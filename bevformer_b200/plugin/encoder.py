@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import linear, linear_relu_dropout
+from .linear import linear, linear_relu_dropout, shared_input_projections
 from .registry import (FEEDFORWARD_NETWORK, HAVE_MMCV, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, _register,
                        build_attention, build_feedforward_network, build_transformer_layer)
 from .spatial_cross_attention import ScaPlan, SpatialCrossAttention
@@ -271,7 +271,9 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                     q_in = q_in0 if i == 0 else None
                     pre = att.attend(query, prev_bev, bev_pos, query_key_padding_mask, ref_2d,
                                      tsa_ss, tsa_lsi, q_in=q_in,
-                                     bev_hw=None if bev_h is None else (bev_h, bev_w))
+                                     bev_hw=None if bev_h is None else (bev_h, bev_w),
+                                     value_pre=kwargs.get("tsa_value_pre"),
+                                     prev_no_grad=bool(kwargs.get("tsa_prev_no_grad", False)))
                     query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1
@@ -287,7 +289,8 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                 if fuse and isinstance(att, SpatialCrossAttention) and query_pos is None:
                     pre = att.attend(query, value if value is not None else key, reference_points_cam,
                                      kwargs.get("bev_mask"), spatial_shapes, level_start_index,
-                                     kwargs.get("sca_plan"), kwargs.get("level_hw_host"))
+                                     kwargs.get("sca_plan"), kwargs.get("level_hw_host"),
+                                     kwargs.get("sca_value_pre"))
                     query = _fused_norm(self.norms[ni], pre, query, att.dropout)
                     ni += 1
                     i += 1
@@ -322,6 +325,11 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                 ni += 1
             i += 1
         return query
+
+
+def key_padding_free(kwargs) -> bool:
+    """No key-padding mask in play (the shared value projections skip the per-layer masked_fill)."""
+    return kwargs.get("key_padding_mask") is None and kwargs.get("query_key_padding_mask") is None
 
 
 class BEVFormerEncoder(nn.Module):
@@ -539,6 +547,26 @@ class BEVFormerEncoder(nn.Module):
         ss = torch.as_tensor(spatial_shapes).to(device=dev, dtype=torch.int64).contiguous()
         lsi = torch.as_tensor(level_start_index).to(device=dev, dtype=torch.int64).contiguous()
 
+        # Every layer projects the SAME camera features (SCA value_proj) and the SAME BEV queue (TSA
+        # value_proj): all of those projections are issued here as one autograd node per shared input, whose
+        # backward chains the input gradients through the GEMM epilogue (plugin/linear.py)
+        sca_pre = tsa_pre = None
+        fusable = [l for l in self.layers if isinstance(l, BEVFormerLayer) and not l.pre_norm
+                   and len(l.attentions) == 2 and isinstance(l.attentions[0], TemporalSelfAttention)
+                   and isinstance(l.attentions[1], SpatialCrossAttention)]
+        if (len(fusable) == len(self.layers) and dev.type == "cuda" and dtype == torch.bfloat16
+                and key_padding_free(kwargs) and value is not None):
+            ncam, s_len, c = value.shape[0], value.shape[1], value.shape[3]
+            feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s_len, c)
+            sca_pre = shared_input_projections(
+                feats, [(l.attentions[1].deformable_attention.value_proj.weight,
+                         l.attentions[1].deformable_attention.value_proj.bias) for l in self.layers])
+            if queue is not None:
+                tsa_pre = shared_input_projections(
+                    queue, [(l.attentions[0].value_proj.weight, l.attentions[0].value_proj.bias)
+                            for l in self.layers])
+        prev_no_grad = prev_bev is not None and bs == 1 and not prev_bev.requires_grad
+
         inter = []
         # the last LayerNorm of layer i also writes (output + bev_pos), the query the temporal
         # self-attention of layer i+1 starts from: no separate add forward, and the two gradients of
@@ -550,6 +578,12 @@ class BEVFormerEncoder(nn.Module):
                 if not isinstance(layer, BEVFormerLayer):
                     carry.pop("q_in", None)
             extra = dict(pos_carry=carry) if isinstance(layer, BEVFormerLayer) else {}
+            if sca_pre is not None:
+                extra["sca_value_pre"] = sca_pre[li]
+            if tsa_pre is not None:
+                extra["tsa_value_pre"] = tsa_pre[li]
+            if isinstance(layer, BEVFormerLayer):
+                extra["tsa_prev_no_grad"] = prev_no_grad
             query = layer(query, key, value, *args, bev_pos=pos, ref_2d=hybrid, ref_3d=None,
                           bev_h=bev_h, bev_w=bev_w, spatial_shapes=ss, level_start_index=lsi,
                           reference_points_cam=ref_cam, bev_mask=bev_mask, prev_bev=queue,

@@ -102,6 +102,61 @@ class _LinearReluDropoutTC(Function):
         return dx, dw, db, None
 
 
+class _SharedInputProjections(Function):
+    """V_l = x W_l^T + b_l for several layers that read the SAME input x (every encoder layer projects the
+    same camera features with its own SCA value_proj, and the same BEV queue with its own TSA value_proj:
+    spatial_cross_attention.py:334, temporal_self_attention.py:198; encoder.py:214-232 never updates
+    either between layers).  One autograd node instead of one per layer: its backward chains the input
+    gradients through the GEMM epilogue (dX = dX_prev + dY_l W_l, bevf_linear_dgrad_acc), so the per-layer
+    gradients of the shared input are never materialised and never summed by element-wise kernels."""
+
+    @staticmethod
+    def forward(ctx, x, *wb):
+        xc = x.contiguous()
+        ws, outs, meta = [], [], []
+        for i in range(0, len(wb), 2):
+            w = wb[i].to(torch.bfloat16)
+            ws.append(w)
+            outs.append(ops.linear_tc(xc, w, wb[i + 1], None, False, torch.bfloat16))
+            meta.append((wb[i].dtype, None if wb[i + 1] is None else wb[i + 1].dtype))
+        ctx.save_for_backward(xc, *ws)
+        ctx.meta = meta
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *dys):
+        xc, *ws = ctx.saved_tensors
+        k = xc.shape[-1]
+        x2 = xc.reshape(-1, k)
+        dx = None
+        grads = []
+        for l, (w, dy, (wdt, bdt)) in enumerate(zip(ws, dys, ctx.meta)):
+            n = w.shape[0]
+            if dy is None:
+                grads += [None, None]
+                continue
+            dy2 = dy.reshape(-1, n).to(torch.bfloat16).contiguous()
+            if ctx.needs_input_grad[0]:
+                dx = ops.linear_dgrad_tc(dy2, w, addend=dx)
+            dw = db = None
+            if ctx.needs_input_grad[1 + 2 * l]:
+                dw, db = _wgrad(dy2, x2, n, k, wdt, bdt)
+            elif bdt is not None and ctx.needs_input_grad[2 + 2 * l]:
+                db = ops.colsum(dy2).to(bdt)
+            grads += [dw, db]
+        return (None if dx is None else dx.view(xc.shape), *grads)
+
+
+def shared_input_projections(x, weights_and_biases):
+    """[x W_l^T + b_l for l] for [(W_l, b_l), ...]; one autograd node on the tcgen05 path (see
+    _SharedInputProjections), plain per-layer projections otherwise."""
+    if all(_use_tc(x, w) for w, _ in weights_and_biases):
+        flat = [t for wb in weights_and_biases for t in wb]
+        return list(_SharedInputProjections.apply(x, *flat))
+    return [linear(x, w, b) for w, b in weights_and_biases]
+
+
 def linear_relu_dropout(x, weight, bias, p: float):
     """FFN hidden layer: Linear -> ReLU -> Dropout(p) (p = 0 outside training)."""
     if _use_tc(x, weight):

@@ -203,11 +203,12 @@ class SpatialCrossAttention(nn.Module):
         nn.init.zeros_(self.output_proj.bias)
 
     def attend(self, query, value, reference_points_cam, bev_mask, spatial_shapes,
-               level_start_index, plan: Optional[ScaPlan] = None, level_hw_host=None):
+               level_start_index, plan: Optional[ScaPlan] = None, level_hw_host=None, value_pre=None):
         """Everything up to and including output_proj, WITHOUT dropout / residual.
         query (bs, Nq, C); value (num_cams, S, bs, C).  ``level_hw_host``: [(h, w), ...] python ints of
         the pyramid, when the caller knows them without a device read: the sampler forward then stages
-        the coarse levels in shared memory through TMA."""
+        the coarse levels in shared memory through TMA.  ``value_pre``: value_proj(value) already computed
+        by the encoder for all layers at once (plugin/linear.py::shared_input_projections)."""
         da = self.deformable_attention
         bs, nq, c = query.shape
         ncam, s = value.shape[0], value.shape[1]
@@ -224,8 +225,10 @@ class SpatialCrossAttention(nn.Module):
         loc, attn = sca_sampling_head(query, w, b, plan.ref_cam, plan.pair_q, plan.pair_cam,
                                       plan.pair_of, ss, bs, nq, m, l, p)
         # value_proj over every camera's feature pyramid (:334), batch-major like the reference
-        feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s, c)
-        v = linear(feats, da.value_proj.weight, da.value_proj.bias).view(bs * ncam, s, m, -1)
+        if value_pre is None:
+            feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s, c)
+            value_pre = linear(feats, da.value_proj.weight, da.value_proj.bias)
+        v = value_pre.view(bs * ncam, s, m, -1)
         staged = None
         if level_hw_host is not None and plan.map_range is not None and len(level_hw_host) == l:
             staged = (level_hw_host, plan.map_range)

@@ -84,7 +84,7 @@ class TemporalSelfAttention(nn.Module):
     # -------------------------------------------------------------------------------------------
     def attend(self, query, value=None, query_pos=None, key_padding_mask=None,
                reference_points=None, spatial_shapes=None, level_start_index=None, q_in=None,
-               bev_hw=None):
+               bev_hw=None, value_pre=None, prev_no_grad=False):
         """Everything up to and including output_proj, batch-first, WITHOUT dropout / identity.
         query (bs, Nq, C); value (bs*2, Nq, C) stacked [prev, cur] or None; ``q_in`` = query +
         query_pos when the caller already has it (the encoder's previous LayerNorm emits it)."""
@@ -95,9 +95,12 @@ class TemporalSelfAttention(nn.Module):
         nv = value.shape[1]
         if q_in is None:
             q_in = query if query_pos is None else query + query_pos
-        # quirk 6: the first bs rows of the stacked queue, whatever they are for bs > 1 (:197)
-        q_cat = torch.cat([value[:bs], q_in], -1)
-        v = linear(value, self.value_proj.weight, self.value_proj.bias)
+        # quirk 6: the first bs rows of the stacked queue, whatever they are for bs > 1 (:197).
+        # prev_no_grad: those rows are the detached history BEV (bs == 1, prev_bev without grad): cutting the
+        # edge here spares the backward a zero-filled (2, Nq, C) gradient, a copy into it and an add
+        head = value[:bs].detach() if prev_no_grad else value[:bs]
+        q_cat = torch.cat([head, q_in], -1)
+        v = value_pre if value_pre is not None else linear(value, self.value_proj.weight, self.value_proj.bias)
         if key_padding_mask is not None:
             v = v.masked_fill(key_padding_mask[..., None], 0.0)
         v = v.reshape(bs * 2, nv, self.num_heads, -1)

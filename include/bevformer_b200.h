@@ -324,6 +324,15 @@ BEVF_API int bevf_linear_dgrad(const void *dy, const void *w, void *dx, int64_t 
                                void *stream);
 
 /*
+ * dX = addend + dY . W : the same kernel with a (M, K) bf16 addend read in the epilogue (may alias dx).
+ * Layers that share an input (the camera features feed every layer's value_proj; the BEV queue feeds every
+ * layer's temporal value_proj) chain their input gradients through it instead of materialising one
+ * gradient per layer and summing them with separate element-wise kernels.
+ */
+BEVF_API int bevf_linear_dgrad_acc(const void *dy, const void *w, const void *addend, void *dx, int64_t M,
+                                   int N, int K, void *stream);
+
+/*
  * Weight gradient of the projection above:  dw[N,K] += dy[M,N]^T . x[M,K]   (fp32, ACCUMULATED
  * INTO: the caller zero-fills).  dy, x bf16 row-major; split over the M rows across the SMs, partial
  * tiles combined with 16 B fp32 reductions.  replaces the cuBLAS call autograd makes for

@@ -330,6 +330,7 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+template <bool kAddend>                    // compile-time: the plain projections pay nothing for the addend path
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_y, const GemmWsParams p) {
@@ -471,20 +472,30 @@ gemm_nt_ws_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 4; ++i) tmem_ld16(taddr + (uint32_t)(c0 + 16 * i), r[i]);
                         tmem_ld_wait();
-                        const int grow = row0 + lane;                 // this thread's output row
-                        const bf16 *arow = (p.addend && grow < p.M)
-                                               ? p.addend + (size_t)grow * p.N + tn * p.BN + c0 : nullptr;
+                        // addend: this thread's output row, 128 contiguous bytes fetched up front
+                        uint4 av[8];
+                        if constexpr (kAddend) {
+                            const int grow = row0 + lane;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) av[i] = make_uint4(0, 0, 0, 0);
+                            if (grow < p.M) {
+                                const uint4 *arow = reinterpret_cast<const uint4 *>(
+                                    p.addend + (size_t)grow * p.N + tn * p.BN + c0);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) av[i] = __ldg(arow + i);
+                            }
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {                 // eight 16 B chunks = 8 columns each
                             float v[8];
-                            uint4 av = make_uint4(0, 0, 0, 0);
-                            if (arow) av = *reinterpret_cast<const uint4 *>(arow + 8 * i);
-                            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int c = 8 * i + j;
                                 float t = __uint_as_float(r[c >> 4][c & 15]) + s_bias[c0 + c];
-                                t += (j & 1) ? bf16_hi(aw[j >> 1]) : bf16_lo(aw[j >> 1]);
+                                if constexpr (kAddend) {
+                                    const uint32_t aw[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
+                                    t += (j & 1) ? bf16_hi(aw[j >> 1]) : bf16_lo(aw[j >> 1]);
+                                }
                                 v[j] = p.relu ? fmaxf(t, 0.f) : t;
                             }
                             uint4 o;
@@ -1042,11 +1053,15 @@ static int launch_ws(const char *who, const void *x, const void *b, const void *
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms_ws, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_nt_ws_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(gemm_nt_ws_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(gemm_nt_ws_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     const int tiles_m = (int)((M + kBM - 1) / kBM);
     const int grid = tiles_m < sms_ws ? tiles_m : sms_ws;
-    gemm_nt_ws_bf16<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, q);
+    if (q.addend)
+        gemm_nt_ws_bf16<true><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, q);
+    else
+        gemm_nt_ws_bf16<false><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_y, q);
     return check_launch(who);
 }
 

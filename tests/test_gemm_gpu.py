@@ -124,3 +124,19 @@ def test_linear_dgrad_tc(case):
     code = DGRAD_SCRIPT.format(root=ROOT, case=case)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 256), (4099, 128, 256), (1000, 256, 512)])
+def test_dgrad_with_addend(M, N, K):
+    """dX = addend + dY W in one launch (bevf_linear_dgrad_acc): the chained input gradient of layers that
+    share an input; checked against fp32 matmul + add, ragged last tile included."""
+    g = torch.Generator().manual_seed(M)
+    dy = torch.randn(M, N, generator=g).to("cuda", torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / N ** 0.5).to("cuda", torch.bfloat16)
+    prev = torch.randn(M, K, generator=g).to("cuda", torch.bfloat16)
+    got = ops.linear_dgrad_tc(dy, w, addend=prev).float()
+    want = dy.float() @ w.float() + prev.float()
+    assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    # and without the addend the plain entry point is unchanged
+    got0 = ops.linear_dgrad_tc(dy, w).float()
+    assert (got0 - dy.float() @ w.float()).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())

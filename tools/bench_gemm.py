@@ -59,9 +59,16 @@ def main():
         tw = timed(lambda: ops.linear_wgrad_tc(dy, x), args.iters, flush)
         tw2 = timed(lambda: ops.linear_wgrad_out(dy, x, torch.bfloat16, True), args.iters, flush)
         tl = timed(lambda: torch.nn.functional.linear(x, w, b), args.iters, flush)
+        td = td_acc = None
+        if N % 64 == 0 and K % 64 == 0:
+            prev = torch.randn(M, K, device=dev).bfloat16()
+            td = timed(lambda: ops.linear_dgrad_tc(dy, w), args.iters, flush)
+            td_acc = timed(lambda: ops.linear_dgrad_tc(dy, w, addend=prev), args.iters, flush)
         byts = M * K * 2 + M * N * (4 if f32 else 2) + N * K * 2
         bw = M * (K + N) * 2 + N * K * 4
         print(json.dumps(dict(shape=name, M=M, N=N, K=K, tc_us=round(t * 1e3, 1), cublas_us=round(tl * 1e3, 1),
+                              dgrad_us=None if td is None else round(td * 1e3, 1),
+                              dgrad_acc_us=None if td_acc is None else round(td_acc * 1e3, 1),
                               wgrad_us=round(tw * 1e3, 1), wgrad_2pass_us=round(tw2 * 1e3, 1), tc_GBs=round(byts / t / 1e6, 1),
                               tc_frac=round(byts / t / 1e6 / hbm, 3), wgrad_frac=round(bw / tw / 1e6 / hbm, 3),
                               tflops=round(2 * M * N * K / t / 1e9, 1))), flush=True)

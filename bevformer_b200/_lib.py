@@ -60,6 +60,7 @@ SIGNATURES = {
     "bevf_linear_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "bevf_linear_wgrad_out": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_int64, c_int64, c_int, c_int,
                                                       c_void_p]),
+    "bevf_sum_tensors": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "bevf_colsum": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "bevf_dropout_inplace": (c_int, [c_void_p, c_int64, ctypes.c_float, ctypes.c_uint64, c_void_p, c_int,
                                      c_void_p]),

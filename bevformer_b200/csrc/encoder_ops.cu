@@ -1223,6 +1223,52 @@ extern "C" int bevf_flatten_feats(const void *feat, const float *cams_embeds, co
     return check_launch(who);
 }
 
+// out = sum of up to 8 equally-shaped bf16 / f32 tensors, fp32 accumulation, one pass (the input gradients
+// of the layers that share an input: n reads + 1 write instead of n-1 pairwise add kernels)
+struct SumPtrs { const void *p[8]; };
+template <typename T>
+__global__ void __launch_bounds__(kEThreads)
+sum_n_kernel(SumPtrs src, int n, T *__restrict__ out, long long vecs) {
+    constexpr int VEC = (sizeof(T) == 2) ? 8 : 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vecs;
+         i += (long long)gridDim.x * blockDim.x) {
+        float acc[VEC];
+        load_vec<T, VEC>(reinterpret_cast<const T *>(src.p[0]) + i * VEC, acc);
+        for (int k = 1; k < n; ++k) {
+            float v[VEC];
+            load_vec<T, VEC>(reinterpret_cast<const T *>(src.p[k]) + i * VEC, v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+        }
+        store_vec<T, VEC>(out + i * VEC, acc);
+    }
+}
+
+extern "C" int bevf_sum_tensors(const void *const *srcs, int n, void *out, int64_t numel, int dtype, void *stream) {
+    const char *who = "bevf_sum_tensors";
+    BEVF_REQUIRE(n >= 1 && n <= 8 && numel >= 0, who, "1..8 tensors");
+    if (numel == 0) return 0;
+    BEVF_REQUIRE(srcs && out, who, "null pointer argument");
+    BEVF_REQUIRE(dtype == BEVF_DTYPE_BF16 || dtype == BEVF_DTYPE_F32, who, "unsupported dtype code");
+    const int vec = dtype == BEVF_DTYPE_BF16 ? 8 : 4;
+    BEVF_REQUIRE(numel % vec == 0, who, "numel must be a multiple of 16 bytes");
+    SumPtrs sp;
+    for (int k = 0; k < 8; ++k) {
+        sp.p[k] = srcs[k < n ? k : 0];
+        BEVF_REQUIRE(sp.p[k] && aligned16(sp.p[k]), who, "source pointers must be non-null and 16-byte aligned");
+    }
+    BEVF_REQUIRE(aligned16(out), who, "out must be 16-byte aligned");
+    const long long vecs = numel / vec;
+    long long blocks = (vecs + kEThreads - 1) / kEThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == BEVF_DTYPE_BF16)
+        sum_n_kernel<bf16><<<(unsigned)blocks, kEThreads, 0, st>>>(sp, n, (bf16 *)out, vecs);
+    else
+        sum_n_kernel<float><<<(unsigned)blocks, kEThreads, 0, st>>>(sp, n, (float *)out, vecs);
+    return check_launch(who);
+}
+
 extern "C" int bevf_colsum(const void *x, float *out, int64_t rows, int C, int dtype, void *stream) {
     const char *who = "bevf_colsum";
     BEVF_REQUIRE(rows >= 0 && C > 0, who, "bad dimension");

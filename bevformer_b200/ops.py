@@ -709,6 +709,26 @@ def linear_wgrad_out(dy, x, grad_dtype, with_bias):
     return dw, db
 
 
+def sum_tensors(ts):
+    """Sum of up to 8 equally-shaped contiguous bf16 / f32 CUDA tensors in one pass (fp32 accumulation)."""
+    import ctypes
+    ts = [t.contiguous() for t in ts]
+    if len(ts) == 1:
+        return ts[0]
+    t0 = ts[0]
+    _need_cuda(t0, "tensors[0]")
+    if len(ts) > 8 or any(t.shape != t0.shape or t.dtype != t0.dtype for t in ts) or t0.dtype not in _DT:
+        raise RuntimeError("sum_tensors: 1..8 tensors of one shape, float32 or bfloat16")
+    out = torch.empty_like(t0)
+    arr = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    lib = _lib.load()
+    with torch.cuda.device(t0.device):
+        st = lib.bevf_sum_tensors(ctypes.addressof(arr), len(ts), out.data_ptr(), t0.numel(), _DT[t0.dtype],
+                                  _stream_ptr(t0))
+    _lib.check(st, lib)
+    return out
+
+
 def colsum(x):
     """fp32 column sums of a (rows, C) tensor (bias gradients)."""
     _need_cuda(x, "x")

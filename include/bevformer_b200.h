@@ -345,6 +345,11 @@ BEVF_API int bevf_linear_wgrad(const void *dy, const void *x, float *dw, float *
 
 /* out[c] += sum over rows of x[r, c]  (fp32, ACCUMULATED INTO).  The bias gradient of the projections:
  * replaces the at::reduce_kernel autograd launches for nn.Linear.bias.grad.  x (rows, C) f32 | bf16. */
+/* out = srcs[0] + ... + srcs[n-1] (n <= 8 device tensors of `numel` elements, bf16 or f32, fp32 accumulation):
+ * the one-pass sum of the per-layer input gradients of a shared input (replaces autograd's chain of
+ * pairwise add kernels).  `srcs` is a HOST array of device pointers. */
+BEVF_API int bevf_sum_tensors(const void *const *srcs, int n, void *out, int64_t numel, int dtype, void *stream);
+
 BEVF_API int bevf_colsum(const void *x, float *out, int64_t rows, int C, int dtype, void *stream);
 
 /*

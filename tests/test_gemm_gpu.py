@@ -6,6 +6,9 @@ import sys
 import textwrap
 
 import pytest
+import torch
+
+from bevformer_b200 import ops
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -140,3 +143,12 @@ def test_dgrad_with_addend(M, N, K):
     # and without the addend the plain entry point is unchanged
     got0 = ops.linear_dgrad_tc(dy, w).float()
     assert (got0 - dy.float() @ w.float()).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
+def test_sum_tensors():
+    g = torch.Generator().manual_seed(0)
+    for dtype, tol in ((torch.float32, 1e-6), (torch.bfloat16, 8e-3)):
+        ts = [torch.randn(1000, 256, generator=g).to("cuda", dtype) for _ in range(6)]
+        got = ops.sum_tensors(ts).float()
+        want = sum(t.float() for t in ts)
+        assert (got - want).abs().max().item() <= tol * max(1.0, want.abs().max().item())

@@ -221,6 +221,129 @@ class PerceptionTransformerBEVEncoder(nn.Module):
         return img.reshape(bs, -1, bev_h * bev_w).permute(0, 2, 1)
 
 
+class _BasicBlock(nn.Module):
+    """mmdet's ResNet BasicBlock (mmdet/models/backbones/resnet.py, 2.14): conv3x3 - norm - ReLU - conv3x3 -
+    norm, + identity (or downsample(x)), ReLU; parameter names conv1 / bn1 / conv2 / bn2 / downsample."""
+
+    def __init__(self, inplanes, planes, norm, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=1, padding=1, bias=False)
+        self.bn1 = norm(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = norm(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        return self.relu(self.bn2(self.conv2(out)) + identity)
+
+
+class ResNetFusion(nn.Module):
+    """BEVFormerV2's temporal fusion (modules/transformerV2.py:16-51): the BEV maps of the configured
+    frames are concatenated along channels, run through ``num_layer`` ResNet basic blocks and projected back
+    to ``out_channels`` with Linear + LayerNorm.  Dense 3x3 convolutions over a 200x200 map: cuDNN work,
+    outside the sampler hot path; kept so that the V2 configs build and run through this package."""
+
+    def __init__(self, in_channels, out_channels, inter_channels, num_layer, norm_cfg=dict(type="SyncBN"),
+                 with_cp=False):
+        super().__init__()
+        typ = (norm_cfg or {}).get("type", "BN")
+        if typ not in ("BN", "BN2d", "SyncBN"):
+            raise KeyError(f"ResNetFusion: unsupported norm {typ}")
+        norm = nn.SyncBatchNorm if typ == "SyncBN" else nn.BatchNorm2d
+        layers = []
+        self.inter_channels = inter_channels
+        for i in range(num_layer):
+            if i == 0 and inter_channels != in_channels:
+                down = nn.Sequential(nn.Conv2d(in_channels, inter_channels, 3, stride=1, padding=1, bias=False),
+                                     norm(inter_channels))
+                layers.append(_BasicBlock(in_channels, inter_channels, norm, down))
+            else:
+                layers.append(_BasicBlock(in_channels if i == 0 else inter_channels, inter_channels, norm))
+        self.layers = nn.Sequential(*layers)
+        self.layer_norm = nn.Sequential(nn.Linear(inter_channels, out_channels), nn.LayerNorm(out_channels))
+        self.with_cp = with_cp
+
+    def forward(self, x):
+        x = torch.cat(x, 1).contiguous()                      # (bs, frames * C, bev_h, bev_w)
+        for layer in self.layers:
+            if self.with_cp and x.requires_grad:
+                x = torch.utils.checkpoint.checkpoint(layer, x)
+            else:
+                x = layer(x)
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)      # nchw -> n (hw) c
+        return self.layer_norm(x)
+
+
+class PerceptionTransformerV2(PerceptionTransformerBEVEncoder):
+    """BEVFormerV2's transformer (modules/transformerV2.py:177-353): the BEV encoder of this package, the
+    optional multi-frame ResNetFusion, and the object-query decoder (plugin/decoder.py).  Same constructor
+    arguments, parameter names and forward contract as the reference class."""
+
+    def __init__(self, num_feature_levels=4, num_cams=6, two_stage_num_proposals=300, encoder=None,
+                 embed_dims=256, use_cams_embeds=True, rotate_center=[100, 100], frames=(0,), decoder=None,
+                 num_fusion=3, inter_channels=None, **kwargs):
+        super().__init__(num_feature_levels, num_cams, two_stage_num_proposals, encoder, embed_dims,
+                         use_cams_embeds, rotate_center, **kwargs)
+        self.decoder = build_transformer_layer_sequence(decoder)
+        self.reference_points = nn.Linear(self.embed_dims, 3)
+        self.frames = frames
+        if len(self.frames) > 1:
+            self.fusion = ResNetFusion(len(self.frames) * self.embed_dims, self.embed_dims,
+                                       inter_channels if inter_channels is not None
+                                       else len(self.frames) * self.embed_dims, num_fusion)
+        self.init_weights()
+
+    def init_weights(self):
+        if not hasattr(self, "reference_points"):
+            return                                             # base-class constructor call
+        super().init_weights()
+        nn.init.xavier_uniform_(self.reference_points.weight)
+        nn.init.zeros_(self.reference_points.bias)
+
+    def get_bev_features(self, mlvl_feats, bev_queries, bev_h, bev_w, grid_length=[0.512, 0.512],
+                         bev_pos=None, prev_bev=None, **kwargs):
+        return super().forward(mlvl_feats, bev_queries, bev_h, bev_w, grid_length, bev_pos, prev_bev, **kwargs)
+
+    def forward(self, mlvl_feats, bev_queries, object_query_embed, bev_h, bev_w, grid_length=[0.512, 0.512],
+                bev_pos=None, reg_branches=None, cls_branches=None, prev_bev=None, **kwargs):
+        """Returns (bev_embed (Nq, bs, C), inter_states, init_reference_out, inter_references_out)
+        (transformerV2.py:243-353).  ``prev_bev``: with several frames, the list of the other frames' BEV
+        maps with None at the current frame's slot (and at missing frames, filled from a neighbour)."""
+        bev_embed = self.get_bev_features(mlvl_feats, bev_queries, bev_h, bev_w, grid_length=grid_length,
+                                          bev_pos=bev_pos, prev_bev=None, **kwargs)
+        if len(self.frames) > 1:
+            cur = list(self.frames).index(0)
+            assert prev_bev[cur] is None and len(prev_bev) == len(self.frames)
+            prev_bev[cur] = bev_embed
+            for i in range(1, cur + 1):                         # missing earlier frames <- the next one
+                if prev_bev[cur - i] is None:
+                    prev_bev[cur - i] = prev_bev[cur - i + 1].detach()
+            for i in range(cur + 1, len(self.frames)):          # missing later frames <- the previous one
+                if prev_bev[i] is None:
+                    prev_bev[i] = prev_bev[i - 1].detach()
+            maps = [x.reshape(x.shape[0], bev_h, bev_w, x.shape[-1]).permute(0, 3, 1, 2).contiguous()
+                    for x in prev_bev]
+            bev_embed = self.fusion(maps)
+        bs = mlvl_feats[0].size(0)
+        query_pos, query = torch.split(object_query_embed, self.embed_dims, dim=1)
+        query_pos = query_pos.unsqueeze(0).expand(bs, -1, -1)
+        query = query.unsqueeze(0).expand(bs, -1, -1)
+        reference_points = self.reference_points(query_pos).sigmoid()
+        init_reference_out = reference_points
+        query = query.permute(1, 0, 2)
+        query_pos = query_pos.permute(1, 0, 2)
+        bev_embed = bev_embed.permute(1, 0, 2)
+        inter_states, inter_references = self.decoder(
+            query=query, key=None, value=bev_embed, query_pos=query_pos, reference_points=reference_points,
+            reg_branches=reg_branches, cls_branches=cls_branches,
+            spatial_shapes=torch.tensor([[bev_h, bev_w]], device=query.device),
+            level_start_index=torch.tensor([0], device=query.device), **kwargs)
+        return bev_embed, inter_states, init_reference_out, inter_references
+
+
 def patch_reference(cls):
     """Install this module's ``get_bev_features`` on the reference's own PerceptionTransformer class
     (which keeps its decoder ``forward``): ``patch_reference(PerceptionTransformer)`` once at import
@@ -233,3 +356,4 @@ def patch_reference(cls):
 
 _register(TRANSFORMER, PerceptionTransformer)
 _register(TRANSFORMER, PerceptionTransformerBEVEncoder)
+_register(TRANSFORMER, PerceptionTransformerV2)

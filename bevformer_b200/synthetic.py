@@ -339,3 +339,56 @@ def make_state_dict(w: Workload, seed: int = 0, trained_like: bool = True, dtype
             sd[p + f"norms.{k}.weight"] = 1.0 + (rn(c, std=0.1) if trained_like else torch.zeros(c))
             sd[p + f"norms.{k}.bias"] = rn(c, std=0.1) if trained_like else torch.zeros(c)
     return {k: v.to(dtype) for k, v in sd.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# generic seeded weights for modules whose state_dict layout is shared with the reference class
+# ------------------------------------------------------------------------------------------------
+def make_random_state_dict(module: torch.nn.Module, seed: int = 0, scale: float = 0.05) -> dict:
+    """Deterministic "trained-like" weights for any module: iterates the state_dict in sorted key order
+    with one seeded generator, so a reference module and its drop-in (same keys and shapes) receive
+    identical values.  LayerNorm-style ``norms.*`` weights are 1 + noise; the ring-shaped
+    ``sampling_offsets.bias`` keeps the module's own (deterministic) initialiser."""
+    g = torch.Generator().manual_seed(31000 + seed)
+    sd = module.state_dict()
+    out = {}
+    for k in sorted(sd):
+        v = sd[k]
+        if k.endswith("sampling_offsets.bias") or not v.is_floating_point():
+            out[k] = v.clone()
+        elif ".norms." in k and k.endswith("weight") or k.endswith("layer_norm.1.weight") or "bn" in k and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("running_var"):
+            out[k] = 0.5 + torch.rand(v.shape, generator=g)
+        elif k.endswith("sampling_offsets.weight"):
+            out[k] = 0.02 * torch.randn(v.shape, generator=g)
+        else:
+            out[k] = scale * torch.randn(v.shape, generator=g)
+    return out
+
+
+DECODER_CFG = dict(
+    type="DetectionTransformerDecoder", num_layers=3, return_intermediate=True,
+    transformerlayers=dict(
+        type="DetrTransformerDecoderLayer",
+        attn_cfgs=[dict(type="MultiheadAttention", embed_dims=256, num_heads=8, dropout=0.1),
+                   dict(type="CustomMSDeformableAttention", embed_dims=256, num_levels=1)],
+        feedforward_channels=512, ffn_dropout=0.1,
+        operation_order=("self_attn", "norm", "cross_attn", "norm", "ffn", "norm")))
+
+
+def make_decoder_inputs(w: Workload, bs: int = 2, num_query: int = 40, seed: int = 0):
+    """Object queries, their positional part, the BEV memory (Nq_bev, bs, C), initial reference points in
+    [0, 1]^3 and seeded regression branches (Linear(C, 10) per layer, the head's reg_branches)."""
+    g = torch.Generator().manual_seed(12000 + seed)
+    c = w.embed_dims
+    query = torch.randn(num_query, bs, c, generator=g)
+    query_pos = torch.randn(num_query, bs, c, generator=g)
+    bev = torch.randn(w.num_query, bs, c, generator=g)
+    ref = torch.rand(bs, num_query, 3, generator=g) * 0.9 + 0.05
+    reg = torch.nn.ModuleList([torch.nn.Linear(c, 10) for _ in range(DECODER_CFG["num_layers"])])
+    with torch.no_grad():
+        for lin in reg:
+            lin.weight.copy_(0.05 * torch.randn(lin.weight.shape, generator=g))
+            lin.bias.copy_(0.05 * torch.randn(lin.bias.shape, generator=g))
+    return query, query_pos, bev, ref, reg

@@ -173,3 +173,50 @@ def test_dropin_backward_on_gpu():
     assert rel_err(v.grad.cpu(), cv.grad) < 2e-3
     for k, p in m.named_parameters():
         assert rel_err(p.grad.cpu(), sdr[k].grad) < 5e-3, k
+
+
+# ------------------------------------------------------------------------------------------------
+# DetectionTransformerDecoder (decoder.py:52-129): the refinement loop around the cross-attention
+# ------------------------------------------------------------------------------------------------
+def _build_decoder():
+    import copy
+    from bevformer_b200 import synthetic as syn
+    from bevformer_b200.plugin import build_transformer_layer_sequence
+    dec = build_transformer_layer_sequence(copy.deepcopy(syn.DECODER_CFG))
+    dec.load_state_dict(syn.make_random_state_dict(dec, 0))
+    return dec
+
+
+def test_decoder_builds_from_config_with_reference_keys():
+    """Same parameter names as the reference decoder built from the same dict (golden 'keys' comes from the
+    reference's own DetectionTransformerDecoder)."""
+    from tests.util import golden
+    dec = _build_decoder()
+    assert sorted(dec.state_dict()) == [str(k) for k in golden("decoder_toy")["keys"]]
+    assert len(dec.layers) == 3 and dec.return_intermediate
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decoder_loop_against_reference_golden(dtype):
+    from bevformer_b200 import synthetic as syn
+    from tests.util import fixed_projection, golden, rel_err
+    g = golden("decoder_toy")
+    w = syn.WORKLOADS["toy"]
+    dec = _build_decoder().to("cuda", dtype).eval()
+    query, query_pos, bev, ref, reg = syn.make_decoder_inputs(w)
+    reg = reg.to("cuda", dtype)
+    q = query.to("cuda", dtype).requires_grad_(True)
+    b = bev.to("cuda", dtype).requires_grad_(True)
+    states, refs = dec(query=q, key=None, value=b, query_pos=query_pos.to("cuda", dtype),
+                       reference_points=ref.to("cuda", dtype), reg_branches=reg, cls_branches=None,
+                       spatial_shapes=torch.tensor([[w.bev_h, w.bev_w]], device="cuda"),
+                       level_start_index=torch.tensor([0], device="cuda"))
+    assert states.shape == g["states"].shape and refs.shape == g["refs"].shape
+    tol = 1e-3 if dtype == torch.float32 else 6e-2
+    assert rel_err(states.float().cpu(), g["states"]) < tol
+    assert rel_err(refs.float().cpu(), g["refs"]) < (1e-4 if dtype == torch.float32 else 2e-2)
+    if dtype == torch.float32:
+        (states * fixed_projection(states.shape).cuda()).sum().backward()
+        assert rel_err(q.grad.cpu(), g["grad_query"]) < 2e-3
+        assert rel_err(b.grad.cpu()[:16], g["grad_bev_rows"]) < 2e-3

@@ -95,3 +95,46 @@ def test_dropin_on_gpu_vs_restatement(aug):
                 img_metas=metas)
     assert got.shape == want.shape
     assert rel_err(got.cpu(), want) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# PerceptionTransformerV2 + ResNetFusion (transformerV2.py:16-51, 177-353)
+# ------------------------------------------------------------------------------------------------
+def _build_v2(w):
+    import copy
+    from bevformer_b200.plugin import PerceptionTransformerV2
+    from tests.golden.make_golden import V2_KW
+    m = PerceptionTransformerV2(num_feature_levels=len(w.levels), num_cams=w.num_cams, encoder=syn.encoder_cfg(w),
+                                decoder=copy.deepcopy(syn.DECODER_CFG), embed_dims=w.embed_dims,
+                                rotate_center=[w.bev_h // 2, w.bev_w // 2], **V2_KW)
+    m.load_state_dict(syn.make_random_state_dict(m, 0))
+    return m
+
+
+def test_v2_parameters_match_reference_class():
+    from tests.util import golden
+    w = syn.WORKLOADS["toy"]
+    m = _build_v2(w)
+    assert sorted(m.state_dict()) == [str(k) for k in golden("v2_toy")["keys"]]
+    assert hasattr(m, "fusion") and len(m.fusion.layers) == 2 and m.fusion.layers[0].downsample is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_v2_forward_against_reference_golden(dtype):
+    from tests.golden.make_golden import grid_length_of, v2_inputs
+    from tests.util import golden, rel_err
+    g = golden("v2_toy")
+    w = syn.WORKLOADS["toy"]
+    m = _build_v2(w).to("cuda", dtype).eval()
+    inp, oq, reg = v2_inputs(w)
+    feats = [f.to("cuda", dtype) for f in inp.mlvl_feats]
+    with torch.no_grad():
+        bev, states, ref0, refs = m(feats, inp.bev_queries.to("cuda", dtype), oq.to("cuda", dtype), w.bev_h, w.bev_w,
+                                    grid_length=list(grid_length_of(w)), bev_pos=inp.bev_pos.to("cuda", dtype),
+                                    reg_branches=reg.to("cuda", dtype), cls_branches=None,
+                                    prev_bev=[inp.prev_bev.to("cuda", dtype), None], img_metas=inp.img_metas)
+    tol = 2e-3 if dtype == torch.float32 else 8e-2     # fp32: cuDNN convolutions (TF32 off) + 9 layers; bf16 encoder-level bar
+    assert rel_err(bev.float().cpu(), g["bev"]) < tol
+    assert rel_err(states.float().cpu(), g["states"]) < tol
+    assert rel_err(ref0.float().cpu(), g["ref0"]) < 1e-2 and rel_err(refs.float().cpu(), g["refs"]) < 3e-2

@@ -215,7 +215,8 @@ def test_decoder_loop_against_reference_golden(dtype):
     assert states.shape == g["states"].shape and refs.shape == g["refs"].shape
     tol = 1e-3 if dtype == torch.float32 else 6e-2
     assert rel_err(states.float().cpu(), g["states"]) < tol
-    assert rel_err(refs.float().cpu(), g["refs"]) < (1e-4 if dtype == torch.float32 else 2e-2)
+    # bf16: the points themselves live in bf16 (2^-9 of [0, 1]) and pass three inverse-sigmoid updates
+    assert rel_err(refs.float().cpu(), g["refs"]) < (1e-4 if dtype == torch.float32 else 5e-2)
     if dtype == torch.float32:
         (states * fixed_projection(states.shape).cuda()).sum().backward()
         assert rel_err(q.grad.cpu(), g["grad_query"]) < 2e-3

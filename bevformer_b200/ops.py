@@ -481,6 +481,9 @@ class LayerNormResidual(Function):
                                             _ptr(sbase), _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         ctx.save_for_backward(x, rc, g, mean, rstd)
+        from .arena import arena_of
+        ctx.arena, ctx.arena_accs = arena_of(gamma, beta)            # flat gradient arena, when enabled
+        ctx.arena_params = (gamma, beta) if ctx.arena is not None else None
         ctx.sbase = sbase                 # the step key of THIS forward (see seed_state)
         ctx.pos_shape = None if pos is None else tuple(pos.shape)
         ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed, pos is not None)
@@ -515,7 +518,11 @@ class LayerNormResidual(Function):
                 dy2 = dy2.contiguous()
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (has_res and drop_p > 0.0) else None
-        dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        if ctx.arena is not None:
+            ctx.arena.touch(*ctx.arena_params)
+            dgb = ctx.arena_accs                                    # accumulate straight into the arena
+        else:
+            dgb = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         with torch.cuda.device(x.device):
             st = lib.bevf_layernorm_backward(x.data_ptr(), _ptr(res), g.data_ptr(), pd, mean.data_ptr(),
@@ -526,6 +533,8 @@ class LayerNormResidual(Function):
                                              _DT[x.dtype], _stream_ptr(x))
         _lib.check(st, lib)
         d_res = None if not has_res else (dres if dres is not None else dx)
+        if ctx.arena is not None:
+            return dx, d_res, None, None, None, None, d_pos
         return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None, d_pos
 
 
@@ -687,6 +696,24 @@ def linear_wgrad_tc(dy, x, with_bias=False, out_dtype=None):
         dw = buf[: N * K].view(N, K)
         db = buf[N * K: N * K + N] if with_bias else None
     return (dw, db) if with_bias else dw
+
+
+def linear_wgrad_into(dy, x, dw_acc, db_acc=None):
+    """dW += dy^T @ x (and db += column sums of dy) accumulated into caller-provided fp32 buffers (the
+    gradient arena): no allocation, no zero-fill, no conversion here."""
+    _need_cuda(dy, "dy")
+    _need_cuda(x, "x")
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.shape[0] != x.shape[0]:
+        raise RuntimeError("linear_wgrad_into: dy (M,N) and x (M,K) must be bfloat16 with equal M")
+    M, N = dy.shape
+    K = x.shape[1]
+    if dw_acc.dtype != torch.float32 or dw_acc.numel() != N * K or not dw_acc.is_contiguous():
+        raise RuntimeError("linear_wgrad_into: dw_acc must be a contiguous fp32 (N, K) buffer")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = lib.bevf_linear_wgrad(dy.data_ptr(), x.data_ptr(), dw_acc.data_ptr(), _ptr(db_acc), M, N, K,
+                                   _stream_ptr(x))
+    _lib.check(st, lib)
 
 
 def linear_wgrad_out(dy, x, grad_dtype, with_bias):

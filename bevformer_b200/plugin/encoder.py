@@ -481,6 +481,28 @@ class BEVFormerEncoder(nn.Module):
             return found
         return None
 
+    def enable_grad_arena(self):
+        """Opt in to the flat gradient arena (bevformer_b200/arena.py): every parameter gradient of the
+        encoder accumulates in one fp32 buffer (one memset per backward pass), is converted once at the end
+        of the pass and handed out as views (``p.grad``).  Gradients are then OVERWRITTEN by each backward
+        pass.  Call after the module sits on its device / dtype; returns the arena (its ``flat_grad(dtype)``
+        is the bucket a data-parallel all-reduce can use directly)."""
+        from ..arena import GradArena
+        seen, groups = set(), []
+        for mod in self.modules():
+            so, aw = getattr(mod, "sampling_offsets", None), getattr(mod, "attention_weights", None)
+            if isinstance(so, nn.Linear) and isinstance(aw, nn.Linear):     # projected as one stacked matrix
+                for grp in ([so.weight, aw.weight], [so.bias, aw.bias]):
+                    if all(id(p) not in seen for p in grp):
+                        groups.append(grp)
+                        seen.update(id(p) for p in grp)
+        for p in self.parameters():
+            if id(p) not in seen:
+                groups.append([p])
+                seen.add(id(p))
+        self._grad_arena = GradArena(groups)
+        return self._grad_arena
+
     def _level_shapes_host(self, spatial_shapes):
         """[(h, w), ...] as python ints, for the TMA tensor maps of the staged sampler.  Lists / CPU tensors
         are read directly; a device tensor is read ONCE (one sync, never during a graph capture) and

@@ -17,11 +17,18 @@ import torch.nn.functional as F
 from torch.autograd.function import Function, once_differentiable
 
 from .. import ops
+from ..arena import arena_of
 
 
 def _use_tc(x: torch.Tensor, weight: torch.Tensor) -> bool:
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight.shape[1] % 64 == 0
             and weight.shape[0] % 16 == 0 and os.environ.get("BEVF_GEMM", "tc") != "cublas")
+
+
+def _arena_ctx(weight, bias):
+    """(arena, accumulators, params) when weight (and bias) accumulate in a gradient arena, else None."""
+    ar, accs = arena_of(weight, bias) if bias is not None else arena_of(weight)
+    return None if ar is None else (ar, accs, (weight, bias))
 
 
 class _LinearTC(Function):
@@ -33,6 +40,7 @@ class _LinearTC(Function):
         ctx.save_for_backward(xc, w, y if relu else None)
         ctx.has_bias = bias is not None
         ctx.dtypes = (weight.dtype, None if bias is None else bias.dtype)
+        ctx.arena = _arena_ctx(weight, bias)
         return y
 
     @staticmethod
@@ -49,14 +57,22 @@ class _LinearTC(Function):
             dx = ops.linear_dgrad_tc(dy2, w).view(x.shape)
         if ctx.needs_input_grad[1]:
             dw, db = _wgrad(dy2, x.reshape(-1, k), n, k, ctx.dtypes[0],
-                            ctx.dtypes[1] if ctx.has_bias else None)
+                            ctx.dtypes[1] if ctx.has_bias else None, ctx.arena)
         elif ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy2).to(ctx.dtypes[1])
         return dx, dw, db, None, None
 
 
-def _wgrad(dy2, x2, n, k, wdtype, bdtype=None):
-    """(dW, db) of a projection; db comes out of the same kernel pass as dW when requested."""
+def _wgrad(dy2, x2, n, k, wdtype, bdtype=None, arena=None):
+    """(dW, db) of a projection; db comes out of the same kernel pass as dW when requested.
+    ``arena`` = (GradArena, [dW accumulator, db accumulator | None], params): accumulate into the flat
+    gradient arena instead and return (None, None) -- the arena hands the gradients over at the end of the
+    backward pass."""
+    if arena is not None and n % 8 == 0:
+        ar, accs, params = arena
+        ar.touch(*[p for p in params if p is not None])
+        ops.linear_wgrad_into(dy2, x2, accs[0].view(n, k), accs[1] if len(accs) > 1 else None)
+        return None, None
     mode = os.environ.get("BEVF_WGRAD", "tc")     # "tc2": two-pass variant (measured slower, profiles/README.md)
     if mode == "tc2" and n % 8 == 0 and wdtype in (torch.bfloat16, torch.float32) and bdtype in (None, wdtype):
         return ops.linear_wgrad_out(dy2, x2, wdtype, bdtype is not None)
@@ -83,6 +99,7 @@ class _LinearReluDropoutTC(Function):
         ops.dropout_inplace_(h, p)
         ctx.save_for_backward(xc, w, h)
         ctx.meta = (bias is not None, weight.dtype, None if bias is None else bias.dtype, float(p))
+        ctx.arena = _arena_ctx(weight, bias)
         return h
 
     @staticmethod
@@ -96,7 +113,7 @@ class _LinearReluDropoutTC(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_dgrad_tc(dz, w).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw, db = _wgrad(dz, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None)
+            dw, db = _wgrad(dz, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None, ctx.arena)
         elif has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dz).to(bdt)
         return dx, dw, db, None
@@ -122,6 +139,7 @@ class _SharedInputProjections(Function):
             meta.append((wb[i].dtype, None if wb[i + 1] is None else wb[i + 1].dtype))
         ctx.save_for_backward(xc, *ws)
         ctx.meta = meta
+        ctx.arenas = [_arena_ctx(wb[i], wb[i + 1]) for i in range(0, len(wb), 2)]
         return tuple(outs)
 
     @staticmethod
@@ -142,7 +160,7 @@ class _SharedInputProjections(Function):
                 dxs.append(ops.linear_dgrad_tc(dy2, w))
             dw = db = None
             if ctx.needs_input_grad[1 + 2 * l]:
-                dw, db = _wgrad(dy2, x2, n, k, wdt, bdt)
+                dw, db = _wgrad(dy2, x2, n, k, wdt, bdt, ctx.arenas[l])
             elif bdt is not None and ctx.needs_input_grad[2 + 2 * l]:
                 db = ops.colsum(dy2).to(bdt)
             grads += [dw, db]
@@ -205,6 +223,7 @@ class _HeadTC(Function):
         ctx.save_for_backward(xc, w, raw)
         ctx.kind, ctx.prep_args = kind, prep_args
         ctx.meta = (bias is not None, weight.dtype, None if bias is None else bias.dtype)
+        ctx.arena = _arena_ctx(weight, bias)
         return loc, attn
 
     @staticmethod
@@ -226,7 +245,7 @@ class _HeadTC(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.linear_dgrad_tc(d_raw, w).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw, db = _wgrad(d_raw, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None)
+            dw, db = _wgrad(d_raw, x.reshape(-1, k), n, k, wdt, bdt if has_bias else None, ctx.arena)
         elif has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(d_raw).to(bdt)
         return dx, dw, db, None, None

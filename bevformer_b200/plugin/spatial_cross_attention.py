@@ -135,8 +135,10 @@ class MSDeformableAttention3D(nn.Module):
 
     def head_weights(self):
         """sampling_offsets and attention_weights stacked into one projection."""
-        return (torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0),
-                torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0))
+        from ..arena import stacked
+        ws, bs_ = (self.sampling_offsets.weight, self.attention_weights.weight), \
+                  (self.sampling_offsets.bias, self.attention_weights.bias)
+        return stacked(ws, torch.cat(ws, 0)), stacked(bs_, torch.cat(bs_, 0))
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,

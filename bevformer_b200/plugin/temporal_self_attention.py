@@ -104,8 +104,10 @@ class TemporalSelfAttention(nn.Module):
         if key_padding_mask is not None:
             v = v.masked_fill(key_padding_mask[..., None], 0.0)
         v = v.reshape(bs * 2, nv, self.num_heads, -1)
-        w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
-        b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+        from ..arena import stacked
+        ws, bs_ = (self.sampling_offsets.weight, self.attention_weights.weight), \
+                  (self.sampling_offsets.bias, self.attention_weights.bias)
+        w, b = stacked(ws, torch.cat(ws, 0)), stacked(bs_, torch.cat(bs_, 0))
 
         ss = torch.as_tensor(spatial_shapes).to(device=query.device, dtype=torch.int64)
         lsi = torch.as_tensor(level_start_index).to(device=query.device, dtype=torch.int64)

@@ -278,3 +278,34 @@ def test_fused_dropout_layernorm_is_consistent():
         assert rel_err(y0.float(), ref0) < tol
         y_again = ops.LayerNormResidual.apply(x.detach(), res.detach(), gamma.detach(), beta.detach(), 1e-5, p)
         assert not torch.equal(y_again, y.detach())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_grad_arena_matches_per_parameter_gradients(dtype):
+    """enable_grad_arena(): the same gradients as the default path (own buffer + conversion per parameter),
+    delivered as views of one flat buffer; two passes in a row (the arena is zeroed per pass, not summed)."""
+    w, enc = _build("tiny", dtype)
+    inp = _inputs(w, 1, True, dtype)
+    proj = fixed_projection((1, w.num_query, 256)).to(DEV, dtype)
+
+    def run():
+        for p in enc.parameters():
+            p.grad = None
+        q = inp.bev_query.detach().requires_grad_(True)
+        out = enc(q, inp.feat, inp.feat, **inp.kwargs())
+        (out * proj).sum().backward()
+        torch.cuda.synchronize()
+        return {k: p.grad.detach().float().clone() for k, p in enc.named_parameters()}, q.grad.float().clone()
+
+    base, qg0 = run()
+    arena = enc.enable_grad_arena()
+    for _ in range(2):
+        got, qg = run()
+        flat = arena.flat_grad(dtype)
+        for k, p in enc.named_parameters():
+            assert p.grad.data_ptr() >= flat.data_ptr() and \
+                p.grad.data_ptr() < flat.data_ptr() + flat.numel() * flat.element_size() or dtype == torch.float32, k
+            ref = base[k]
+            tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+            assert (got[k] - ref).abs().max().item() <= tol * max(1e-3, ref.abs().max().item()), k
+        assert (qg - qg0).abs().max().item() <= 1e-3 * max(1.0, qg0.abs().max().item())

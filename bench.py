@@ -232,7 +232,7 @@ def run_ours(args):
     params = [p for p in enc.parameters()]
     # graph mode: all parameter gradients accumulate in one flat arena (one memset + one conversion per step
     # instead of ~150 small fills / casts); its bf16 result is also the all-reduce bucket
-    arena = enc.enable_grad_arena() if (use_graph and do_bwd and not args.no_arena) else None
+    arena = enc.enable_grad_arena(overlap=not args.no_overlap) if (use_graph and do_bwd and not args.no_arena) else None
 
     def allreduce_grads():
         """Graph-replayed step: one flat-bucket NCCL all-reduce (eager mode uses torch DDP instead)."""
@@ -533,6 +533,7 @@ def run_ours(args):
                           if flush_l2 else
                           "per-step working set (>1 GB of activations + 95 MB features) exceeds the 126 MB L2; no explicit flush"),
                    "gradients": ("flat fp32 gradient arena: one memset + one conversion per step (bevformer_b200/arena.py)"
+                                 + ("" if args.no_overlap else "; weight-gradient GEMMs on a side stream, joined at the end of the backward pass")
                                  if arena is not None else "one fp32 buffer + conversion per parameter"),
                    "gemm_backend": ("cuBLASLt via torch (library GEMM; BEVF_GEMM=cublas)"
                                     if os.environ.get("BEVF_GEMM", "tc") == "cublas" else
@@ -556,6 +557,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-standin", action="store_true", help="skip the grid_sample-on-GPU stand-in leg")
     ap.add_argument("--no-arena", action="store_true", help="per-parameter gradient buffers instead of the flat arena")
+    ap.add_argument("--no-overlap", action="store_true", help="weight-gradient GEMMs on the main stream")
     ap.add_argument("--config", default="base", choices=sorted(CONFIGS),
                     help="BASELINE.json config to run (default: base = the headline metric)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")

@@ -46,6 +46,13 @@ class GradArena:
                     for dt in dtypes}
         self.active = False
         self.touched: set = set()
+        # Weight gradients feed nothing but this arena, so they are off the backward's critical path: with
+        # ``side_stream`` set (enable_grad_arena(overlap=True)) every weight-gradient GEMM is issued on that
+        # stream, behind an event of the launching stream, and the end-of-backward conversion waits for it.
+        # The memory-bound dW GEMMs then run under the L2-reduction-bound sampler backward and the other
+        # main-stream kernels instead of after them.  Capturable: the side stream forks from and joins the
+        # capturing stream inside the pass.
+        self.side_stream = None
         for p in params:
             p._bevf_acc = self.acc_view(p)
             p._bevf_arena = self
@@ -85,8 +92,25 @@ class GradArena:
             for m in getattr(t, "_bevf_members", (t,)):      # a stacked weight stands for its member parameters
                 self.touched.add(id(m))
 
+    def run_off_critical_path(self, fn, *inputs) -> None:
+        """Launch ``fn()`` (kernels that only accumulate into this arena) on the side stream when there is
+        one, ordered after everything already queued on the current stream; otherwise inline."""
+        if self.side_stream is None:
+            fn()
+            return
+        main = torch.cuda.current_stream(self.acc.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side_stream.wait_event(ev)
+        with torch.cuda.stream(self.side_stream):
+            fn()
+        for t in inputs:                                   # the allocator must not recycle them early
+            t.record_stream(self.side_stream)
+
     def _finalize(self) -> None:
         self.active = False
+        if self.side_stream is not None:
+            torch.cuda.current_stream(self.acc.device).wait_stream(self.side_stream)
         for dt, buf in self.out.items():
             if buf is not self.acc:
                 buf.copy_(self.acc)                                   # the one conversion of the step

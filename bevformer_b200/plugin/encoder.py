@@ -481,12 +481,13 @@ class BEVFormerEncoder(nn.Module):
             return found
         return None
 
-    def enable_grad_arena(self):
+    def enable_grad_arena(self, overlap: bool = False):
         """Opt in to the flat gradient arena (bevformer_b200/arena.py): every parameter gradient of the
         encoder accumulates in one fp32 buffer (one memset per backward pass), is converted once at the end
         of the pass and handed out as views (``p.grad``).  Gradients are then OVERWRITTEN by each backward
         pass.  Call after the module sits on its device / dtype; returns the arena (its ``flat_grad(dtype)``
-        is the bucket a data-parallel all-reduce can use directly)."""
+        is the bucket a data-parallel all-reduce can use directly).  ``overlap``: issue the weight-gradient
+        GEMMs on a side stream (they feed nothing but the arena), joined at the end of the backward pass."""
         from ..arena import GradArena
         seen, groups = set(), []
         for mod in self.modules():
@@ -501,6 +502,8 @@ class BEVFormerEncoder(nn.Module):
                 groups.append([p])
                 seen.add(id(p))
         self._grad_arena = GradArena(groups)
+        if overlap:
+            self._grad_arena.side_stream = torch.cuda.Stream(self._grad_arena.acc.device)
         return self._grad_arena
 
     def _level_shapes_host(self, spatial_shapes):

@@ -71,7 +71,8 @@ def _wgrad(dy2, x2, n, k, wdtype, bdtype=None, arena=None):
     if arena is not None and n % 8 == 0:
         ar, accs, params = arena
         ar.touch(*[p for p in params if p is not None])
-        ops.linear_wgrad_into(dy2, x2, accs[0].view(n, k), accs[1] if len(accs) > 1 else None)
+        dw_acc, db_acc = accs[0].view(n, k), (accs[1] if len(accs) > 1 else None)
+        ar.run_off_critical_path(lambda: ops.linear_wgrad_into(dy2, x2, dw_acc, db_acc), dy2, x2)
         return None, None
     mode = os.environ.get("BEVF_WGRAD", "tc")     # "tc2": two-pass variant (measured slower, profiles/README.md)
     if mode == "tc2" and n % 8 == 0 and wdtype in (torch.bfloat16, torch.float32) and bdtype in (None, wdtype):

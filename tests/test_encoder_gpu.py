@@ -280,8 +280,9 @@ def test_fused_dropout_layernorm_is_consistent():
         assert not torch.equal(y_again, y.detach())
 
 
+@pytest.mark.parametrize("overlap", [False, True])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_grad_arena_matches_per_parameter_gradients(dtype):
+def test_grad_arena_matches_per_parameter_gradients(dtype, overlap):
     """enable_grad_arena(): the same gradients as the default path (own buffer + conversion per parameter),
     delivered as views of one flat buffer; two passes in a row (the arena is zeroed per pass, not summed)."""
     w, enc = _build("tiny", dtype)
@@ -298,7 +299,7 @@ def test_grad_arena_matches_per_parameter_gradients(dtype):
         return {k: p.grad.detach().float().clone() for k, p in enc.named_parameters()}, q.grad.float().clone()
 
     base, qg0 = run()
-    arena = enc.enable_grad_arena()
+    arena = enc.enable_grad_arena(overlap=overlap)
     for _ in range(2):
         got, qg = run()
         flat = arena.flat_grad(dtype)

@@ -309,4 +309,5 @@ def test_grad_arena_matches_per_parameter_gradients(dtype, overlap):
             ref = base[k]
             tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
             assert (got[k] - ref).abs().max().item() <= tol * max(1e-3, ref.abs().max().item()), k
-        assert (qg - qg0).abs().max().item() <= 1e-3 * max(1.0, qg0.abs().max().item())
+        # (run-to-run: the sampler's reductions are unordered, one bf16 ulp may flip)
+        assert (qg - qg0).abs().max().item() <= (1e-2 if dtype == torch.bfloat16 else 1e-3) * max(1.0, qg0.abs().max().item())

@@ -130,7 +130,7 @@ class _SharedInputProjections(Function):
     -- was measured slower: the epilogue's per-row addend loads stall the TMEM drain, 107 us vs 41 + 44.)"""
 
     @staticmethod
-    def forward(ctx, x, *wb):
+    def forward(ctx, state, x, *wb):
         xc = x.contiguous()
         ws, outs, meta = [], [], []
         for i in range(0, len(wb), 2):
@@ -141,32 +141,77 @@ class _SharedInputProjections(Function):
         ctx.save_for_backward(xc, *ws)
         ctx.meta = meta
         ctx.arenas = [_arena_ctx(wb[i], wb[i + 1]) for i in range(0, len(wb), 2)]
+        ctx.state = state
+        # what the early (gradient-hook) path needs, kept outside autograd's saved tensors
+        state.update(x2=xc.reshape(-1, xc.shape[-1]), ws=ws, meta=meta, arenas=ctx.arenas,
+                     early=[None] * len(ws), need_dx=x.requires_grad)
         return tuple(outs)
+
+    @staticmethod
+    def early(state, l, dy):
+        """Gradient hook of output l: with an overlap-enabled arena, this layer's dX and dW / db are issued
+        on the side stream the moment its output gradient exists (right after that layer's sampler backward)
+        instead of when the whole node runs at the end of the pass -- they then execute under the following
+        layers' backward.  Returns nothing: the node's backward picks the results up."""
+        ar = state["arenas"][l]
+        if ar is None or ar[0].side_stream is None or state["early"][l] is not None:
+            return
+        arena = ar[0]
+        w = state["ws"][l]
+        n, k = w.shape
+        wdt, bdt = state["meta"][l]
+        dy2 = dy.reshape(-1, n).to(torch.bfloat16).contiguous()
+        box = {}
+
+        def work():
+            if state["need_dx"]:
+                box["dx"] = ops.linear_dgrad_tc(dy2, w)
+            dw_acc, db_acc = ar[1][0].view(n, k), (ar[1][1] if len(ar[1]) > 1 else None)
+            ops.linear_wgrad_into(dy2, state["x2"], dw_acc, db_acc)
+
+        arena.touch(*[p for p in ar[2] if p is not None])
+        arena.run_off_critical_path(work, dy2, state["x2"], w)
+        state["early"][l] = box
 
     @staticmethod
     @once_differentiable
     def backward(ctx, *dys):
         xc, *ws = ctx.saved_tensors
+        state = ctx.state
         k = xc.shape[-1]
         x2 = xc.reshape(-1, k)
         dxs = []
         grads = []
+        joined = False
         for l, (w, dy, (wdt, bdt)) in enumerate(zip(ws, dys, ctx.meta)):
             n = w.shape[0]
             if dy is None:
                 grads += [None, None]
                 continue
+            box = state["early"][l]
+            if box is not None:                                  # done ahead of time on the side stream
+                if "dx" in box:
+                    if not joined:
+                        side = ctx.arenas[l][0].side_stream
+                        torch.cuda.current_stream(xc.device).wait_stream(side)
+                        joined = True
+                    dxs.append(box["dx"])
+                grads += [None, None]
+                continue
             dy2 = dy.reshape(-1, n).to(torch.bfloat16).contiguous()
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[1]:
                 dxs.append(ops.linear_dgrad_tc(dy2, w))
             dw = db = None
-            if ctx.needs_input_grad[1 + 2 * l]:
+            if ctx.needs_input_grad[2 + 2 * l]:
                 dw, db = _wgrad(dy2, x2, n, k, wdt, bdt, ctx.arenas[l])
-            elif bdt is not None and ctx.needs_input_grad[2 + 2 * l]:
+            elif bdt is not None and ctx.needs_input_grad[3 + 2 * l]:
                 db = ops.colsum(dy2).to(bdt)
             grads += [dw, db]
         dx = ops.sum_tensors(dxs).view(xc.shape) if dxs else None
-        return (dx, *grads)
+        for t in dxs:
+            t.record_stream(torch.cuda.current_stream(xc.device))
+        state["early"] = [None] * len(ws)
+        return (None, dx, *grads)
 
 
 def shared_input_projections(x, weights_and_biases):
@@ -174,7 +219,12 @@ def shared_input_projections(x, weights_and_biases):
     _SharedInputProjections), plain per-layer projections otherwise."""
     if all(_use_tc(x, w) for w, _ in weights_and_biases):
         flat = [t for wb in weights_and_biases for t in wb]
-        return list(_SharedInputProjections.apply(x, *flat))
+        state = {}
+        outs = list(_SharedInputProjections.apply(state, x, *flat))
+        if torch.is_grad_enabled() and any(o.requires_grad for o in outs):
+            for l, o in enumerate(outs):
+                o.register_hook(lambda g, l=l: _SharedInputProjections.early(state, l, g))
+        return outs
     return [linear(x, w, b) for w, b in weights_and_biases]
 
 

@@ -15,6 +15,7 @@ each of the three blocks.
 from __future__ import annotations
 
 import copy
+import os
 import warnings
 from typing import Optional
 
@@ -503,7 +504,9 @@ class BEVFormerEncoder(nn.Module):
                 seen.add(id(p))
         self._grad_arena = GradArena(groups)
         if overlap:
-            self._grad_arena.side_stream = torch.cuda.Stream(self._grad_arena.acc.device)
+            # high priority: its CTAs take SM resources as soon as CTAs of the running main-stream kernel retire
+            prio = int(os.environ.get("BEVF_SIDE_PRIORITY", "-1"))
+            self._grad_arena.side_stream = torch.cuda.Stream(self._grad_arena.acc.device, priority=prio)
         return self._grad_arena
 
     def _level_shapes_host(self, spatial_shapes):

@@ -504,8 +504,7 @@ class BEVFormerEncoder(nn.Module):
                 seen.add(id(p))
         self._grad_arena = GradArena(groups)
         if overlap:
-            # high priority: its CTAs take SM resources as soon as CTAs of the running main-stream kernel retire
-            prio = int(os.environ.get("BEVF_SIDE_PRIORITY", "-1"))
+            prio = int(os.environ.get("BEVF_SIDE_PRIORITY", "0"))     # (measured: -1 brings nothing)
             self._grad_arena.side_stream = torch.cuda.Stream(self._grad_arena.acc.device, priority=prio)
         return self._grad_arena
 

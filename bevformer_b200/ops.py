@@ -295,6 +295,7 @@ class SamplerRows(Function):
             out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         ctx.group_order = group_order
+        ctx.value_early = getattr(value, "_bevf_early", None)     # see plugin/linear.py::shared_input_projections
         return out
 
     @staticmethod
@@ -303,6 +304,9 @@ class SamplerRows(Function):
         value, loc, attn, row_map, ss, ls = ctx.saved_tensors
         gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(),
                                         group_order=ctx.group_order)
+        if ctx.value_early is not None and ctx.value_early(gv):
+            # the producer of `value` took the fp32 gradient (conversion + its GEMMs run off the critical path)
+            return None, gl, ga, None, None, None, None, None
         return gv.to(value.dtype), gl, ga, None, None, None, None, None
 
 

@@ -155,23 +155,25 @@ class _SharedInputProjections(Function):
         layers' backward.  Returns nothing: the node's backward picks the results up."""
         ar = state["arenas"][l]
         if ar is None or ar[0].side_stream is None or state["early"][l] is not None:
-            return
+            return False
         arena = ar[0]
         w = state["ws"][l]
         n, k = w.shape
         wdt, bdt = state["meta"][l]
-        dy2 = dy.reshape(-1, n).to(torch.bfloat16).contiguous()
         box = {}
 
         def work():
+            # (the fp32 -> bf16 conversion of a sampler's grad_value happens here too, off the critical path)
+            dy2 = dy.reshape(-1, n).to(torch.bfloat16).contiguous()
             if state["need_dx"]:
                 box["dx"] = ops.linear_dgrad_tc(dy2, w)
             dw_acc, db_acc = ar[1][0].view(n, k), (ar[1][1] if len(ar[1]) > 1 else None)
             ops.linear_wgrad_into(dy2, state["x2"], dw_acc, db_acc)
 
         arena.touch(*[p for p in ar[2] if p is not None])
-        arena.run_off_critical_path(work, dy2, state["x2"], w)
+        arena.run_off_critical_path(work, dy, state["x2"], w)
         state["early"][l] = box
+        return True
 
     @staticmethod
     @once_differentiable
@@ -185,10 +187,10 @@ class _SharedInputProjections(Function):
         joined = False
         for l, (w, dy, (wdt, bdt)) in enumerate(zip(ws, dys, ctx.meta)):
             n = w.shape[0]
-            if dy is None:
+            box = state["early"][l]
+            if box is None and dy is None:
                 grads += [None, None]
                 continue
-            box = state["early"][l]
             if box is not None:                                  # done ahead of time on the side stream
                 if "dx" in box:
                     if not joined:
@@ -223,7 +225,10 @@ def shared_input_projections(x, weights_and_biases):
         outs = list(_SharedInputProjections.apply(state, x, *flat))
         if torch.is_grad_enabled() and any(o.requires_grad for o in outs):
             for l, o in enumerate(outs):
-                o.register_hook(lambda g, l=l: _SharedInputProjections.early(state, l, g))
+                o.register_hook(lambda g, l=l: (_SharedInputProjections.early(state, l, g), None)[1])
+                # consumers that produce this output's gradient themselves (the sampler: fp32 grad_value) may
+                # hand it over directly and skip autograd's dtype conversion on the critical path
+                o._bevf_early = (lambda g, l=l: _SharedInputProjections.early(state, l, g))
         return outs
     return [linear(x, w, b) for w, b in weights_and_biases]
 

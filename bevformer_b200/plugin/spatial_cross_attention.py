@@ -231,6 +231,8 @@ class SpatialCrossAttention(nn.Module):
             feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s, c)
             value_pre = linear(feats, da.value_proj.weight, da.value_proj.bias)
         v = value_pre.view(bs * ncam, s, m, -1)
+        if hasattr(value_pre, "_bevf_early"):
+            v._bevf_early = value_pre._bevf_early
         staged = None
         if level_hw_host is not None and plan.map_range is not None and len(level_hw_host) == l:
             staged = (level_hw_host, plan.map_range)

@@ -103,7 +103,10 @@ class TemporalSelfAttention(nn.Module):
         v = value_pre if value_pre is not None else linear(value, self.value_proj.weight, self.value_proj.bias)
         if key_padding_mask is not None:
             v = v.masked_fill(key_padding_mask[..., None], 0.0)
+        early = getattr(v, "_bevf_early", None)
         v = v.reshape(bs * 2, nv, self.num_heads, -1)
+        if early is not None and key_padding_mask is None:
+            v._bevf_early = early
         from ..arena import stacked
         ws, bs_ = (self.sampling_offsets.weight, self.attention_weights.weight), \
                   (self.sampling_offsets.bias, self.attention_weights.bias)

@@ -278,6 +278,15 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     return grad_value, grad_loc, grad_attn
 
 
+# Second stream for work that is off the critical path (weight gradients, zero-fills and projections that
+# are needed later): set by BEVFormerEncoder.enable_grad_arena(overlap=True); None = everything in order.
+AUX_STREAM: dict = {}
+
+
+def aux_stream(device):
+    return AUX_STREAM.get(torch.device(device))
+
+
 class SamplerRows(Function):
     """Sampler over a compact list of query rows (SCA's in-view (camera, query) pairs)."""
 
@@ -296,13 +305,32 @@ class SamplerRows(Function):
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         ctx.group_order = group_order
         ctx.value_early = getattr(value, "_bevf_early", None)     # see plugin/linear.py::shared_input_projections
+        ctx.gv_zero = None
+        aux = aux_stream(value.device)
+        if aux is not None and value.requires_grad and torch.is_grad_enabled():
+            # the backward accumulates grad_value into a zero-filled fp32 buffer: fill it NOW on the second
+            # stream (it overlaps the forward) instead of on the backward's critical path
+            main = torch.cuda.current_stream(value.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            aux.wait_event(ev)
+            with torch.cuda.stream(aux):
+                gv0 = torch.zeros(value.shape, device=value.device, dtype=torch.float32)
+                done = torch.cuda.Event()
+                done.record(aux)
+            gv0.record_stream(main)
+            ctx.gv_zero = (gv0, done)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
         value, loc, attn, row_map, ss, ls = ctx.saved_tensors
-        gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(),
+        gv0 = None
+        if ctx.gv_zero is not None:
+            gv0, done = ctx.gv_zero
+            torch.cuda.current_stream(value.device).wait_event(done)
+        gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
                                         group_order=ctx.group_order)
         if ctx.value_early is not None and ctx.value_early(gv):
             # the producer of `value` took the fp32 gradient (conversion + its GEMMs run off the critical path)

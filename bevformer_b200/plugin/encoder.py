@@ -506,6 +506,7 @@ class BEVFormerEncoder(nn.Module):
         if overlap:
             prio = int(os.environ.get("BEVF_SIDE_PRIORITY", "0"))     # (measured: -1 brings nothing)
             self._grad_arena.side_stream = torch.cuda.Stream(self._grad_arena.acc.device, priority=prio)
+            ops.AUX_STREAM[torch.device(self._grad_arena.acc.device)] = self._grad_arena.side_stream
         return self._grad_arena
 
     def _level_shapes_host(self, spatial_shapes):

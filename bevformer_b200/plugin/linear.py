@@ -133,11 +133,33 @@ class _SharedInputProjections(Function):
     def forward(ctx, state, x, *wb):
         xc = x.contiguous()
         ws, outs, meta = [], [], []
+        # layer l needs its projection only when layer l runs: with a second stream they are all issued there
+        # now and each consumer waits for its own (state["ready"][l]) -- the projections of the later layers
+        # run under the earlier layers' forward
+        aux = ops.aux_stream(xc.device)
+        main = torch.cuda.current_stream(xc.device) if aux is not None else None
+        ready = []
+        if aux is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            aux.wait_event(ev)
         for i in range(0, len(wb), 2):
             w = wb[i].to(torch.bfloat16)
             ws.append(w)
-            outs.append(ops.linear_tc(xc, w, wb[i + 1], None, False, torch.bfloat16))
+            if aux is None:
+                outs.append(ops.linear_tc(xc, w, wb[i + 1], None, False, torch.bfloat16))
+            else:
+                with torch.cuda.stream(aux):
+                    o = ops.linear_tc(xc, w, wb[i + 1], None, False, torch.bfloat16)
+                    e = torch.cuda.Event()
+                    e.record(aux)
+                o.record_stream(main)
+                outs.append(o)
+                ready.append(e)
             meta.append((wb[i].dtype, None if wb[i + 1] is None else wb[i + 1].dtype))
+        if aux is not None:
+            xc.record_stream(aux)
+        state["ready"] = ready
         ctx.save_for_backward(xc, *ws)
         ctx.meta = meta
         ctx.arenas = [_arena_ctx(wb[i], wb[i + 1]) for i in range(0, len(wb), 2)]
@@ -229,6 +251,9 @@ def shared_input_projections(x, weights_and_biases):
                 # consumers that produce this output's gradient themselves (the sampler: fp32 grad_value) may
                 # hand it over directly and skip autograd's dtype conversion on the critical path
                 o._bevf_early = (lambda g, l=l: _SharedInputProjections.early(state, l, g))
+        for l, o in enumerate(outs):
+            if state.get("ready"):
+                o._bevf_ready = state["ready"][l]
         return outs
     return [linear(x, w, b) for w, b in weights_and_biases]
 

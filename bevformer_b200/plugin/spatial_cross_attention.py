@@ -230,6 +230,8 @@ class SpatialCrossAttention(nn.Module):
         if value_pre is None:
             feats = value.permute(2, 0, 1, 3).reshape(bs * ncam, s, c)
             value_pre = linear(feats, da.value_proj.weight, da.value_proj.bias)
+        if getattr(value_pre, "_bevf_ready", None) is not None:       # produced on the second stream
+            torch.cuda.current_stream(value_pre.device).wait_event(value_pre._bevf_ready)
         v = value_pre.view(bs * ncam, s, m, -1)
         if hasattr(value_pre, "_bevf_early"):
             v._bevf_early = value_pre._bevf_early

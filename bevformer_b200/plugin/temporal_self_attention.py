@@ -101,6 +101,8 @@ class TemporalSelfAttention(nn.Module):
         head = value[:bs].detach() if prev_no_grad else value[:bs]
         q_cat = torch.cat([head, q_in], -1)
         v = value_pre if value_pre is not None else linear(value, self.value_proj.weight, self.value_proj.bias)
+        if getattr(v, "_bevf_ready", None) is not None:               # produced on the second stream
+            torch.cuda.current_stream(v.device).wait_event(v._bevf_ready)
         if key_padding_mask is not None:
             v = v.masked_fill(key_padding_mask[..., None], 0.0)
         early = getattr(v, "_bevf_early", None)

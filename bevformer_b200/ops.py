@@ -307,7 +307,8 @@ class SamplerRows(Function):
         ctx.value_early = getattr(value, "_bevf_early", None)     # see plugin/linear.py::shared_input_projections
         ctx.gv_zero = None
         aux = aux_stream(value.device)
-        if aux is not None and value.requires_grad and torch.is_grad_enabled():
+        if (aux is not None and value.requires_grad and torch.is_grad_enabled()
+                and os.environ.get("BEVF_AUX_FILL", "1") == "1"):
             # the backward accumulates grad_value into a zero-filled fp32 buffer: fill it NOW on the second
             # stream (it overlaps the forward) instead of on the backward's critical path
             main = torch.cuda.current_stream(value.device)

@@ -53,6 +53,10 @@ class GradArena:
         # main-stream kernels instead of after them.  Capturable: the side stream forks from and joins the
         # capturing stream inside the pass.
         self.side_stream = None
+        # data parallel: set to True when the caller averages the fp32 accumulator over the ranks itself
+        # (all_reduce_mean) -- the conversion to the parameter dtype then happens after the all-reduce, so
+        # gradients are averaged in fp32 like the reference's DDP does, not in bf16
+        self.defer_conversion = False
         for p in params:
             p._bevf_acc = self.acc_view(p)
             p._bevf_arena = self
@@ -111,15 +115,27 @@ class GradArena:
         self.active = False
         if self.side_stream is not None:
             torch.cuda.current_stream(self.acc.device).wait_stream(self.side_stream)
-        for dt, buf in self.out.items():
-            if buf is not self.acc:
-                buf.copy_(self.acc)                                   # the one conversion of the step
+        if not self.defer_conversion:
+            self.convert()
         for p in self.params:
             if id(p) not in self.touched:
                 continue
             view = self.grad_view(p)
             if p.grad is None or p.grad.data_ptr() != view.data_ptr():
                 p.grad = view
+
+    def convert(self) -> None:
+        for dt, buf in self.out.items():
+            if buf is not self.acc:
+                buf.copy_(self.acc)                                   # the one conversion of the step
+
+    def all_reduce_mean(self, world_size: int, group=None) -> None:
+        """Average the fp32 accumulator over the process group with ONE all-reduce (19.8 MB for the base
+        encoder), then convert once: the data-parallel exchange of a step (requires defer_conversion)."""
+        import torch.distributed as dist
+        dist.all_reduce(self.acc, group=group)
+        self.acc.div_(world_size)
+        self.convert()
 
     def flat_grad(self, dtype) -> torch.Tensor:
         return self.out[dtype]

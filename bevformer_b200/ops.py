@@ -308,9 +308,10 @@ class SamplerRows(Function):
         ctx.gv_zero = None
         aux = aux_stream(value.device)
         if (aux is not None and value.requires_grad and torch.is_grad_enabled()
-                and os.environ.get("BEVF_AUX_FILL", "1") == "1"):
+                and os.environ.get("BEVF_AUX_FILL", "0") == "1"):
             # the backward accumulates grad_value into a zero-filled fp32 buffer: fill it NOW on the second
-            # stream (it overlaps the forward) instead of on the backward's critical path
+            # stream (it overlaps the forward) instead of on the backward's critical path.  Measured neutral on
+            # B200 (15.70 vs 15.73 ms) and it holds 1.6 GB from forward to backward: opt-in (BEVF_AUX_FILL=1)
             main = torch.cuda.current_stream(value.device)
             ev = torch.cuda.Event()
             ev.record(main)

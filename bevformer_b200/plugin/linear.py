@@ -135,8 +135,8 @@ class _SharedInputProjections(Function):
         ws, outs, meta = [], [], []
         # layer l needs its projection only when layer l runs: with a second stream they are all issued there
         # now and each consumer waits for its own (state["ready"][l]) -- the projections of the later layers
-        # run under the earlier layers' forward
-        aux = ops.aux_stream(xc.device) if os.environ.get("BEVF_AUX_PROJ", "1") == "1" else None
+        # run under the earlier layers' forward.  Measured neutral on B200: opt-in (BEVF_AUX_PROJ=1)
+        aux = ops.aux_stream(xc.device) if os.environ.get("BEVF_AUX_PROJ", "0") == "1" else None
         main = torch.cuda.current_stream(xc.device) if aux is not None else None
         ready = []
         if aux is not None:

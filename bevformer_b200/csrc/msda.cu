@@ -129,7 +129,9 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const float *__restrict__ attn, const TG *__restrict__ grad_out,
              float *__restrict__ grad_value, float *__restrict__ grad_loc,
              float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M, int Q,
-             int L, int P, int magic, int iters, long long rows) {
+             int L, int P, int magic, int iters, long long rows, unsigned red_skip) {
+    // red_skip: bit l set = the grad_value contributions of level l are NOT scattered here (hybrid mode: the
+    // coarse levels go through msda_bwd_splat_d32, which merges them in registers, on a second stream)
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
     constexpr bool kHalfDot = (VEC == 8) && (sizeof(TG) == 2);
     __shared__ LevelTab tab;
@@ -233,6 +235,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             }
             // scatter w * a * g with 16 B reductions; zero-weight corners are skipped
             if constexpr (!kScatter) {
+            } else if ((red_skip >> l) & 1u) {
             } else if constexpr (!kPaired) {
                 float *gp = grad_value + o00;
                 if (q00 != 0.f) red_add_v4(gp, q00 * gra[0], q00 * gra[1], q00 * gra[2], q00 * gra[3]);
@@ -456,7 +459,7 @@ static int bwd_split_enabled() {
     int v = g_bwd_mode.load(std::memory_order_relaxed);
     if (v < 0) {
         const char *e = getenv("BEVF_MSDA_BWD");
-        v = (e && e[0] == 's') ? 1 : 0;
+        v = (e && e[0] == 's') ? 1 : 0;               // (mode 2 needs its stream: only through the setter)
         g_bwd_mode.store(v, std::memory_order_relaxed);
     }
     return v;
@@ -470,10 +473,18 @@ static unsigned splat_direct_mask() {
     return (unsigned)v;
 }
 
+// second stream + events for the hybrid backward (created by bevf_msda_set_backward_mode(2), i.e. outside any
+// stream capture; the fork / join below is capturable)
+static cudaStream_t g_side_stream = nullptr;
+constexpr int kSideEvents = 64;
+static cudaEvent_t g_side_events[kSideEvents];
+static std::atomic<unsigned> g_side_ev_next{0};
+
 template <typename TG>
 static int launch_splat(const char *who, const float *loc, const float *attn, const void *go, float *gv,
                         const int *row_map, const int *order, const int64_t *hw, const int64_t *ls,
-                        int S, int M, int Q, int L, int P, long long pairs, cudaStream_t st) {
+                        int S, int M, int Q, int L, int P, long long pairs, unsigned level_mask,
+                        cudaStream_t st) {
     const size_t smem = splat_smem_bytes(M, sizeof(TG));
     static bool attr_done = false;                     // per instantiation
     if (!attr_done) {
@@ -486,7 +497,8 @@ static int launch_splat(const char *who, const float *loc, const float *attn, co
     }
     const unsigned grid = (unsigned)((pairs + kSplatG - 1) / kSplatG);
     msda_bwd_splat_d32<TG><<<grid, 32 * M, smem, st>>>(loc, attn, (const TG *)go, gv, row_map, order, hw,
-                                                       ls, S, M, Q, L, P, pairs, splat_direct_mask());
+                                                       ls, S, M, Q, L, P, pairs, splat_direct_mask(),
+                                                       level_mask);
     return check_launch(who);
 }
 
@@ -500,18 +512,37 @@ static int launch_bwd(const char *who, const void *value, const int64_t *hw, con
         const int iters = pick_iters(rows, G);
         const long long per_block = (long long)(kThreads / 32) * G * iters;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
-        const bool split = bwd_split_enabled() && M <= kSplatMaxHeads && S * (long long)M * 32 < (1ll << 31);
-        if (split) {
+        const int mode = bwd_split_enabled();
+        const bool can_split = M <= kSplatMaxHeads && S * (long long)M * 32 < (1ll << 31);
+        if (mode == 1 && can_split) {
             if (int e = launch_splat<TG>(who, loc, attn, go, gv, row_map, order, hw, ls, S, M, Q, L, P,
-                                         rows / M, st))
+                                         rows / M, 0xffffffffu, st))
                 return e;
             msda_bwd_d32<T, TG, false><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
                                                                   (const TG *)go, gv, gl, ga, row_map, S, M,
-                                                                  Q, L, P, (65536 + P - 1) / P, iters, rows);
+                                                                  Q, L, P, (65536 + P - 1) / P, iters, rows, 0u);
+        } else if (mode == 2 && can_split && L >= 2 && g_side_stream) {
+            // hybrid: the coarse half of the pyramid (most collisions, 47 % of the reduction bytes at base)
+            // through the register-merging splat on the second stream, everything else in the one-kernel
+            // backward on the caller's stream; the two write disjoint levels of grad_value
+            unsigned coarse = 0;
+            for (int l = L / 2; l < L; ++l) coarse |= 1u << l;
+            cudaEvent_t fork = g_side_events[g_side_ev_next.fetch_add(1) % kSideEvents];
+            cudaEvent_t join = g_side_events[g_side_ev_next.fetch_add(1) % kSideEvents];
+            cudaEventRecord(fork, st);
+            cudaStreamWaitEvent(g_side_stream, fork, 0);
+            if (int e = launch_splat<TG>(who, loc, attn, go, gv, row_map, order, hw, ls, S, M, Q, L, P,
+                                         rows / M, coarse, g_side_stream))
+                return e;
+            cudaEventRecord(join, g_side_stream);
+            msda_bwd_d32<T, TG, true><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
+                                                                 (const TG *)go, gv, gl, ga, row_map, S, M,
+                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows, coarse);
+            cudaStreamWaitEvent(st, join, 0);
         } else {
             msda_bwd_d32<T, TG, true><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
                                                                  (const TG *)go, gv, gl, ga, row_map, S, M,
-                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows);
+                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows, 0u);
         }
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
@@ -613,7 +644,16 @@ extern "C" int bevf_msda_rows_backward(const void *value, int value_dtype, const
 }
 
 extern "C" int bevf_msda_set_backward_mode(int mode) {
-    if (mode != 0 && mode != 1) return fail("%s: mode must be 0 (one kernel) or 1 (split)", "bevf_msda_set_backward_mode");
+    if (mode < 0 || mode > 2)
+        return fail("%s: mode must be 0 (one kernel), 1 (split) or 2 (hybrid)", "bevf_msda_set_backward_mode");
+    if (mode == 2 && !g_side_stream) {
+        if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            g_side_stream = nullptr;
+            return fail("%s: cannot create the second stream", "bevf_msda_set_backward_mode");
+        }
+        for (int i = 0; i < kSideEvents; ++i) cudaEventCreateWithFlags(&g_side_events[i], cudaEventDisableTiming);
+    }
     g_bwd_mode.store(mode, std::memory_order_relaxed);
     return 0;
 }

@@ -67,7 +67,8 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
                    const TG *__restrict__ grad_out, float *__restrict__ grad_value,
                    const int *__restrict__ row_map, const int *__restrict__ order,
                    const int64_t *__restrict__ level_hw, const int64_t *__restrict__ level_start,
-                   int S, int M, int Q, int L, int P, long long pairs, unsigned direct_mask) {
+                   int S, int M, int Q, int L, int P, long long pairs, unsigned direct_mask,
+                   unsigned level_mask) {
     extern __shared__ __align__(16) unsigned char splat_smem[];
     const int C = M * 32;
     TG *gs = reinterpret_cast<TG *>(splat_smem);                                   // [kSplatG][C]
@@ -111,6 +112,7 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
     const unsigned FULL = 0xffffffffu;
 
     for (int l = 0; l < L; ++l) {
+        if (!((level_mask >> l) & 1u)) continue;        // hybrid mode: the other levels are scattered by msda_bwd_d32
         const int H = tab.h[l], W = tab.w[l];
         const long long lofs = tab.lofs[l];
         const bool direct_level = (direct_mask >> l) & 1u;

@@ -161,6 +161,8 @@ BEVF_API int bevf_msda_rows_forward_staged(const void *value, int value_dtype, c
  * variable BEVF_MSDA_BWD=split).  0: one kernel, one 16 B-vector L2 reduction per corner contribution.
  * 1: gather kernel + a splat kernel that merges the contributions of 64 neighbouring rows in registers
  * before they reach L2 (fewer reductions, more instructions; kept for A/B measurements).
+ * 2: hybrid -- the coarse half of the pyramid through the splat kernel on a library-owned second stream
+ * (forked from / joined to the caller's stream with events: capturable), the rest in the one kernel.
  * Results agree up to fp32 summation order.
  */
 BEVF_API int bevf_msda_set_backward_mode(int mode);

@@ -151,7 +151,7 @@ def test_base_shapes_properties(which):
     assert rel_err(ga.cpu(), rga) < 1e-3 and rel_err(gl.cpu(), rgl) < 1e-3
 
 
-@pytest.fixture(params=[0, 1], ids=["bwd_one_kernel", "bwd_split"])
+@pytest.fixture(params=[0, 1, 2], ids=["bwd_one_kernel", "bwd_split", "bwd_hybrid"])
 def backward_mode(request):
     """Both grad_value strategies of the library (bevf_msda_set_backward_mode) must pass the same bars."""
     from bevformer_b200 import _lib

@@ -110,6 +110,9 @@ def main():
     args = ap.parse_args()
     dev = "cuda"
     w = syn.WORKLOADS["base"]
+    if os.environ.get("BENCH_BWD_MODE"):
+        from bevformer_b200 import _lib
+        assert _lib.load().bevf_msda_set_backward_mode(int(os.environ["BENCH_BWD_MODE"])) == 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     shapes = {
         "tsa_base": dict(bs=2, levels=[(200, 200)], nq=40000, pts=4),

@@ -458,6 +458,29 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    if args.breakdown and rank == 0:
+        # development aid, after both timed loops: CUPTI kernel records of 3 more replays of the same step
+        # (warm caches, real overlap with the side stream) grouped by kernel name
+        import collections
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step_resident()
+            torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0.0, 0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                a = agg[ev.name[:150]]
+                a[0] += ev.device_time
+                a[1] += 1
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][0])
+        with open(args.breakdown, "w") as f:
+            f.write(f"sum of kernel durations per step: {sum(v[0] for _, v in rows) / 3e3:.3f} ms over "
+                    f"{sum(v[1] for _, v in rows) // 3} launches (step wall time {ms:.3f} ms; side-stream "
+                    f"kernels overlap)\n")
+            for name, (us, n) in rows:
+                f.write(f"{us / 3e3:8.3f} ms {n // 3:5d}x {us / n:8.1f} us  {name}\n")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -556,6 +579,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-standin", action="store_true", help="skip the grid_sample-on-GPU stand-in leg")
+    ap.add_argument("--breakdown", default=None, metavar="PATH",
+                    help="after the timed loops, write a per-kernel table (CUPTI) of 3 more steps to PATH")
     ap.add_argument("--no-arena", action="store_true", help="per-parameter gradient buffers instead of the flat arena")
     ap.add_argument("--no-overlap", action="store_true", help="weight-gradient GEMMs on the main stream")
     ap.add_argument("--config", default="base", choices=sorted(CONFIGS),

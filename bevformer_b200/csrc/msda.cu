@@ -480,15 +480,14 @@ constexpr int kSideEvents = 64;
 static cudaEvent_t g_side_events[kSideEvents];
 static std::atomic<unsigned> g_side_ev_next{0};
 
-template <typename TG>
-static int launch_splat(const char *who, const float *loc, const float *attn, const void *go, float *gv,
-                        const int *row_map, const int *order, const int64_t *hw, const int64_t *ls,
-                        int S, int M, int Q, int L, int P, long long pairs, unsigned level_mask,
-                        cudaStream_t st) {
-    const size_t smem = splat_smem_bytes(M, sizeof(TG));
+template <typename TG, int kM>
+static int launch_splat_km(const char *who, const float *loc, const float *attn, const void *go, float *gv,
+                           const int *row_map, const int *order, const int64_t *hw, const int64_t *ls,
+                           int S, int M, int Q, int L, int P, long long pairs, unsigned level_mask,
+                           cudaStream_t st) {
     static bool attr_done = false;                     // per instantiation
     if (!attr_done) {
-        if (cudaFuncSetAttribute(msda_bwd_splat_d32<TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(msda_bwd_splat_d32<TG, kM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)splat_smem_bytes(kSplatMaxHeads, sizeof(TG))) != cudaSuccess) {
             cudaGetLastError();
             return fail("%s: cannot reserve shared memory for the splat kernel", who);
@@ -496,10 +495,23 @@ static int launch_splat(const char *who, const float *loc, const float *attn, co
         attr_done = true;
     }
     const unsigned grid = (unsigned)((pairs + kSplatG - 1) / kSplatG);
-    msda_bwd_splat_d32<TG><<<grid, 32 * M, smem, st>>>(loc, attn, (const TG *)go, gv, row_map, order, hw,
-                                                       ls, S, M, Q, L, P, pairs, splat_direct_mask(),
-                                                       level_mask);
+    msda_bwd_splat_d32<TG, kM><<<grid, 32 * M, splat_smem_bytes(M, sizeof(TG)), st>>>(
+        loc, attn, (const TG *)go, gv, row_map, order, hw, ls, S, M, Q, L, P, pairs, splat_direct_mask(),
+        level_mask);
     return check_launch(who);
+}
+
+template <typename TG>
+static int launch_splat(const char *who, const float *loc, const float *attn, const void *go, float *gv,
+                        const int *row_map, const int *order, const int64_t *hw, const int64_t *ls,
+                        int S, int M, int Q, int L, int P, long long pairs, unsigned level_mask,
+                        cudaStream_t st) {
+    // the head count of every BEVFormer config is 8: that instance addresses the window with immediates
+    if (M == 8)
+        return launch_splat_km<TG, 8>(who, loc, attn, go, gv, row_map, order, hw, ls, S, M, Q, L, P, pairs,
+                                      level_mask, st);
+    return launch_splat_km<TG, 0>(who, loc, attn, go, gv, row_map, order, hw, ls, S, M, Q, L, P, pairs,
+                                  level_mask, st);
 }
 
 template <typename T, typename TG>

@@ -37,6 +37,8 @@ constexpr int kSplatMaxHeads = 8;
 struct __align__(16) SplatStage {                 // per warp
     float4 w[kChunk][kSplatG];                    // attention-scaled corner weights {00, 01, 10, 11}
     int cell[kChunk][kSplatG];                    // (y0 + 1) << 16 | (x0 + 1), -1 = sample out of the map
+    float4 lw[kSplatG];                           // the members of the current window pass, compacted:
+    unsigned lm[kSplatG];                         //   weights, (byte offset of the row's grad_out << 8) | window position
 };
 
 __device__ __forceinline__ void red_add_f32(float *p, float v) {
@@ -61,7 +63,8 @@ template <> __device__ __forceinline__ void splat_g4<bf16>(const bf16 *p, float 
 #include "msda_splat_switch.inc"   // BEVF_SPLAT_DISPATCH: one brx.idx jump table (tools/gen_splat_switch.py)
 static_assert(kWX == 10 && kWY == 5, "msda_splat_switch.inc is generated for a 10 x 5 window");
 
-template <typename TG>
+// kM: the head count when known at compile time (row pitch C = 32 kM becomes an immediate), 0 = run time.
+template <typename TG, int kM>
 __global__ void __launch_bounds__(32 * kSplatMaxHeads, 2)
 msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn,
                    const TG *__restrict__ grad_out, float *__restrict__ grad_value,
@@ -70,7 +73,7 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
                    int S, int M, int Q, int L, int P, long long pairs, unsigned direct_mask,
                    unsigned level_mask) {
     extern __shared__ __align__(16) unsigned char splat_smem[];
-    const int C = M * 32;
+    const int C = kM ? kM * 32 : M * 32;
     TG *gs = reinterpret_cast<TG *>(splat_smem);                                   // [kSplatG][C]
     SplatStage *stages = reinterpret_cast<SplatStage *>(splat_smem + (size_t)kSplatG * C * sizeof(TG));
     __shared__ int row_s[kSplatG], map_s[kSplatG];
@@ -110,6 +113,7 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
     const float *att0 = attn + ((long long)max(r0, 0) * M + m) * LP;
     const float *att1 = attn + ((long long)max(r1, 0) * M + m) * LP;
     const unsigned FULL = 0xffffffffu;
+    const char *gbytes = reinterpret_cast<const char *>(gcol + lane);      // + row byte offset = this lane's channel
 
     for (int l = 0; l < L; ++l) {
         if (!((level_mask >> l) & 1u)) continue;        // hybrid mode: the other levels are scattered by msda_bwd_d32
@@ -119,38 +123,55 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
         for (int p0 = 0; p0 < P; p0 += kChunk) {
             const int nsl = min(kChunk, P - p0);
             // ---- lay out the samples of up to kChunk slices: lane k <-> rows k and k + 32
+            // lay out the samples of up to kChunk slices; lane k <-> rows k and k + 32, one row at a time (the
+            // register window stays live across this code: keep the transient state small).  16 B loads when
+            // the chunk is a whole aligned group of four points.
+            const int sbase = l * P + p0;
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-                if (j < nsl) {
-                    int cell0 = -1, cell1 = -1;
-                    const int s = l * P + p0 + j;
-                    float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
-                    if (r0 >= 0) {
-                        const float2 xy = __ldg(loc0 + s);
-                        const float a = __ldg(att0 + s);
-                        const Corner c = make_corner(xy.x, xy.y, H, W);
-                        if (c.valid) {
-                            cell0 = ((c.y0 + 1) << 16) | (c.x0 + 1);
-                            wa = make_float4(c.w00 * a, c.w01 * a, c.w10 * a, c.w11 * a);
-                        }
+            for (int half = 0; half < 2; ++half) {
+                const int rr = half ? r1 : r0;
+                const float2 *lp = (half ? loc1 : loc0) + sbase;
+                const float *ap = (half ? att1 : att0) + sbase;
+                float2 xy[kChunk];
+                float at[kChunk];
+                if (rr >= 0) {
+                    if (nsl == kChunk && (P & 3) == 0) {
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(lp));
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(lp) + 1);
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(ap));
+                        xy[0] = make_float2(a.x, a.y); xy[1] = make_float2(a.z, a.w);
+                        xy[2] = make_float2(b.x, b.y); xy[3] = make_float2(b.z, b.w);
+                        at[0] = t.x; at[1] = t.y; at[2] = t.z; at[3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j)
+                            if (j < nsl) { xy[j] = __ldg(lp + j); at[j] = __ldg(ap + j); }
                     }
-                    if (r1 >= 0) {
-                        const float2 xy = __ldg(loc1 + s);
-                        const float a = __ldg(att1 + s);
-                        const Corner c = make_corner(xy.x, xy.y, H, W);
-                        if (c.valid) {
-                            cell1 = ((c.y0 + 1) << 16) | (c.x0 + 1);
-                            wb = make_float4(c.w00 * a, c.w01 * a, c.w10 * a, c.w11 * a);
+                }
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                    if (j < nsl) {
+                        int cell = -1;
+                        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rr >= 0) {
+                            const Corner c = make_corner(xy[j].x, xy[j].y, H, W);
+                            if (c.valid) {
+                                cell = ((c.y0 + 1) << 16) | (c.x0 + 1);
+                                wv = make_float4(c.w00 * at[j], c.w01 * at[j], c.w10 * at[j], c.w11 * at[j]);
+                            }
                         }
+                        st.w[j][lane + 32 * half] = wv;
+                        st.cell[j][lane + 32 * half] = cell;
                     }
-                    st.w[j][lane] = wa; st.w[j][lane + 32] = wb;
-                    st.cell[j][lane] = cell0; st.cell[j][lane + 32] = cell1;
                 }
             }
             __syncwarp();
             // ---- one slice at a time
 #pragma unroll 1
             for (int j = 0; j < nsl; ++j) {
+                float acc[kCells];                       // the register window; every flush leaves it zero
+#pragma unroll
+                for (int i = 0; i < kCells; ++i) acc[i] = 0.f;
                 const int c0 = st.cell[j][lane], c1 = st.cell[j][lane + 32];
                 const int x0a = (c0 & 0xffff) - 1, y0a = (c0 >> 16) - 1;       // garbage when c0 < 0 (masked)
                 const int x0b = (c1 & 0xffff) - 1, y0b = (c1 >> 16) - 1;
@@ -198,31 +219,53 @@ msda_bwd_splat_d32(const float *__restrict__ loc, const float *__restrict__ attn
                                              (unsigned)(y0b - oy) < (unsigned)kWY;
                             const unsigned mem0 = __ballot_sync(FULL, me0), mem1 = __ballot_sync(FULL, me1);
                             if (!(mem0 | mem1)) continue;
-                            const int rel0 = (y0a - oy) * kWX + (x0a - ox);
-                            const int rel1 = (y0b - oy) * kWX + (x0b - ox);
-                            float acc[kCells];
-#pragma unroll
-                            for (int i = 0; i < kCells; ++i) acc[i] = 0.f;
-                            for (int half = 0; half < 2; ++half) {
-                                for (unsigned mm = half ? mem1 : mem0; mm; mm &= mm - 1) {
-                                    const int kk = __ffs(mm) - 1;
-                                    const int k = kk + 32 * half;
-                                    const int c = __shfl_sync(FULL, half ? rel1 : rel0, kk);
-                                    const float4 w = st.w[j][k];
-                                    const float g = splat_g1<TG>(gcol + k * C + lane);
-                                    BEVF_SPLAT_DISPATCH(acc, w, g, c);
-                                }
+                            // compact the members into the pass list: position = rank among the members
+                            const unsigned lt = (1u << lane) - 1u;
+                            const int n0 = __popc(mem0), n = n0 + __popc(mem1);
+                            if (me0) {
+                                const int pos = __popc(mem0 & lt);
+                                st.lw[pos] = st.w[j][lane];
+                                st.lm[pos] = ((unsigned)(lane * C * (int)sizeof(TG)) << 8) |
+                                             (unsigned)((y0a - oy) * kWX + (x0a - ox));
                             }
-                            // ---- flush: one full-line reduction per touched cell
+                            if (me1) {
+                                const int pos = n0 + __popc(mem1 & lt);
+                                st.lw[pos] = st.w[j][lane + 32];
+                                st.lm[pos] = ((unsigned)((lane + 32) * C * (int)sizeof(TG)) << 8) |
+                                             (unsigned)((y0b - oy) * kWX + (x0b - ox));
+                            }
+                            __syncwarp();
+                            // apply: sequential entries, two per trip (independent loads ahead of each dispatch)
+                            int e = 0;
+                            for (; e + 2 <= n; e += 2) {
+                                const float4 w0 = st.lw[e], w1 = st.lw[e + 1];
+                                const unsigned m0 = st.lm[e], m1 = st.lm[e + 1];
+                                const float g0 = splat_g1<TG>(reinterpret_cast<const TG *>(gbytes + (m0 >> 8)));
+                                const float g1 = splat_g1<TG>(reinterpret_cast<const TG *>(gbytes + (m1 >> 8)));
+                                { const int c = (int)(m0 & 0xffu); BEVF_SPLAT_DISPATCH(acc, w0, g0, c); }
+                                { const int c = (int)(m1 & 0xffu); BEVF_SPLAT_DISPATCH(acc, w1, g1, c); }
+                            }
+                            if (e < n) {
+                                const float4 w0 = st.lw[e];
+                                const unsigned m0 = st.lm[e];
+                                const float g0 = splat_g1<TG>(reinterpret_cast<const TG *>(gbytes + (m0 >> 8)));
+                                const int c = (int)(m0 & 0xffu);
+                                BEVF_SPLAT_DISPATCH(acc, w0, g0, c);
+                            }
+                            __syncwarp();                                   // the list is rewritten by the next pass
+                            // ---- flush: one full-line reduction per touched cell, which is zeroed on the way
 #pragma unroll
                             for (int cy = 0; cy < kWYP; ++cy) {
+                                const int y = oy + cy;
+                                const bool yok = (unsigned)y < (unsigned)H;
+                                // one address per window row; the cells of the row sit C floats apart
+                                float *rowp = gbase + ((long long)y * W + ox) * C + lane;
 #pragma unroll
                                 for (int cx = 0; cx < kWXP; ++cx) {
                                     const float v = acc[cy * kWXP + cx];
                                     if (__any_sync(FULL, v != 0.f)) {
-                                        const int x = ox + cx, y = oy + cy;
-                                        if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
-                                            red_add_f32(gbase + (long long)(y * W + x) * C + lane, v);
+                                        if (yok && (unsigned)(ox + cx) < (unsigned)W) red_add_f32(rowp + cx * C, v);
+                                        acc[cy * kWXP + cx] = 0.f;
                                     }
                                 }
                             }

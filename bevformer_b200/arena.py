@@ -57,7 +57,15 @@ class GradArena:
         # (all_reduce_mean) -- the conversion to the parameter dtype then happens after the all-reduce, so
         # gradients are averaged in fp32 like the reference's DDP does, not in bf16
         self.defer_conversion = False
+        # The parameter VALUES move into flat buffers with the same offsets (p.data becomes a view): the
+        # members of an adjacency group then already form the stacked matrix their module projects with, and
+        # `stacked` hands out a view instead of launching a torch.cat per forward pass.
+        self.pflat = {dt: torch.empty(off, device=dev, dtype=dt) for dt in dtypes}
         for p in params:
+            o = self.offset[id(p)]
+            home = self.pflat[p.dtype][o:o + p.numel()].view(p.shape)
+            home.copy_(p.data)
+            p.data = home
             p._bevf_acc = self.acc_view(p)
             p._bevf_arena = self
 
@@ -141,15 +149,31 @@ class GradArena:
         return self.out[dtype]
 
 
-def stacked(params, dim0_cat: torch.Tensor) -> torch.Tensor:
-    """Tag ``dim0_cat`` (= torch.cat(params, 0)) with the arena accumulator that spans its members, when they
-    lie adjacently in one arena; returns the tensor."""
+def stacked(params, direct: bool = False) -> torch.Tensor:
+    """torch.cat(params, 0) for parameters a module projects with as ONE matrix, tagged with the arena
+    accumulator that spans them.  ``direct``: the caller guarantees that the consumer accumulates the
+    gradient into the arena itself (plugin/linear.py's tcgen05 nodes) -- then, while the parameters still
+    live adjacently in the arena's flat value buffer, the result is a VIEW of that buffer (no kernel): a leaf
+    that requires grad and never receives one through autograd."""
     ar = getattr(params[0], "_bevf_arena", None)
-    if ar is not None and all(getattr(p, "_bevf_arena", None) is ar for p in params):
-        span = ar.span_view(params, dim0_cat.shape)
-        if span is not None:
-            dim0_cat._bevf_arena, dim0_cat._bevf_acc, dim0_cat._bevf_members = ar, span, tuple(params)
-    return dim0_cat
+    if ar is None or any(getattr(p, "_bevf_arena", None) is not ar for p in params):
+        return torch.cat(params, 0)
+    shape = (sum(p.shape[0] for p in params),) + tuple(params[0].shape[1:])
+    span = ar.span_view(params, shape)
+    if span is None:
+        return torch.cat(params, 0)
+    out = None
+    if direct and shape[0] % 8 == 0:
+        flat = ar.pflat[params[0].dtype]
+        o, es = ar.offset[id(params[0])], flat.element_size()
+        if all(p.dtype == flat.dtype and p.data_ptr() == flat.data_ptr() + ar.offset[id(p)] * es for p in params):
+            out = flat[o:o + span.numel()].view(shape)
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                out.requires_grad_(True)
+    if out is None:
+        out = torch.cat(params, 0)
+    out._bevf_arena, out._bevf_acc, out._bevf_members = ar, span, tuple(params)
+    return out
 
 
 def arena_of(*tensors):

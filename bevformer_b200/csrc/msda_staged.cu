@@ -217,9 +217,11 @@ msda_fwd_staged_d32(const __grid_constant__ StagedMaps maps, const StagedInfo in
                         const unsigned short hb = (unsigned short)(half ? (qb >> 16) : (qb & 0xffffu));
                         vt.axpy_h(ht, acc); vb.axpy_h(hb, acc);
                     } else {
-                        const float qt = __shfl_sync(0xffffffffu, half ? w01 : w00, src);
-                        const float qb = __shfl_sync(0xffffffffu, half ? w11 : w10, src);
-                        vt.axpy(qt, acc); vb.axpy(qb, acc);
+                        // the column is the READER's: fetch both and pick here (the source lane's own
+                        // `half` says nothing about which column this lane accumulates)
+                        const float q00 = __shfl_sync(0xffffffffu, w00, src), q01 = __shfl_sync(0xffffffffu, w01, src);
+                        const float q10 = __shfl_sync(0xffffffffu, w10, src), q11 = __shfl_sync(0xffffffffu, w11, src);
+                        vt.axpy(half ? q01 : q00, acc); vb.axpy(half ? q11 : q10, acc);
                     }
                 }
             }

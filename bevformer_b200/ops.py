@@ -482,10 +482,13 @@ class LayerNormResidual(Function):
     """y = LayerNorm(dropout_p(x) + residual) * gamma + beta (fp32 statistics); residual may be None.
     The dropout keep-mask is regenerated from a Philox seed in backward (nothing stored).
     With ``pos`` the kernel also writes y + pos (the next block's positional-encoded query) and the
-    call returns (y, y + pos); their two gradients are summed inside the backward kernel."""
+    call returns (y, y + pos); their two gradients are summed inside the backward kernel.
+    With ``twin`` the call returns (y, y') where y' aliases y: the caller feeds y to the next block and y'
+    to that block's residual connection, so their two gradients arrive separately and are summed inside
+    the backward kernel too (autograd would otherwise add them with a three-pass elementwise kernel)."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, eps, drop_p=0.0, pos=None):
+    def forward(ctx, x, residual, gamma, beta, eps, drop_p=0.0, pos=None, twin=False):
         _need_cuda(x, "x")
         if x.dtype not in _DT:
             raise RuntimeError("layernorm: float32 or bfloat16 only")
@@ -521,6 +524,8 @@ class LayerNormResidual(Function):
         ctx.sbase = sbase                 # the step key of THIS forward (see seed_state)
         ctx.pos_shape = None if pos is None else tuple(pos.shape)
         ctx.meta = (residual is not None, gamma.dtype, beta.dtype, pd, float(drop_p), seed, pos is not None)
+        if pos is None and twin:
+            return y, y.view(y.shape)
         return y if pos is None else (y, y2)
 
     @staticmethod
@@ -568,8 +573,8 @@ class LayerNormResidual(Function):
         _lib.check(st, lib)
         d_res = None if not has_res else (dres if dres is not None else dx)
         if ctx.arena is not None:
-            return dx, d_res, None, None, None, None, d_pos
-        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None, d_pos
+            return dx, d_res, None, None, None, None, d_pos, None
+        return dx, d_res, dgb[0].to(gdt), dgb[1].to(bdt), None, None, d_pos, None
 
 
 class ScaCombine(Function):

@@ -113,18 +113,24 @@ if not HAVE_MMCV:
     _register(FEEDFORWARD_NETWORK, FFN, name="FFN")
 
 
-def _fused_norm(norm: nn.LayerNorm, x, residual, dropout: Optional[nn.Dropout] = None, pos=None):
+def _fused_norm(norm: nn.LayerNorm, x, residual, dropout: Optional[nn.Dropout] = None, pos=None,
+                twin: bool = False):
     """LayerNorm(dropout(x) + residual) in one kernel (fp32 statistics; the dropout of the block
     that produced x is applied inside, active only in training mode).  With ``pos`` the kernel also
-    emits y + pos and the call returns (y, y + pos).  Shapes / dtypes the kernel does not cover
+    emits y + pos and the call returns (y, y + pos); with ``twin`` it returns (y, alias of y) so that the
+    next block and its residual connection receive separate gradients (summed inside the backward kernel
+    instead of by autograd).  Shapes / dtypes the kernel does not cover
     (fp16 activations under the reference's fp16 configs, embed_dims other than 256 / 512) take the
     unfused CUDA ops instead."""
     if x.dtype not in (torch.float32, torch.bfloat16) or x.shape[-1] not in (256, 512):
         h = x if dropout is None else dropout(x)
         y = norm(h if residual is None else h + residual)
+        if pos is None and twin:
+            return y, y
         return y if pos is None else (y, y + pos)
     p = dropout.p if (dropout is not None and dropout.training) else 0.0
-    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps, p, pos)
+    return ops.LayerNormResidual.apply(x.contiguous(), residual, norm.weight, norm.bias, norm.eps, p, pos,
+                                       twin and pos is None)
 
 
 class MyCustomBaseTransformerLayer(nn.Module):
@@ -263,9 +269,14 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
             tsa_ss = torch.tensor([[bev_h, bev_w]], device=query.device)
             tsa_lsi = torch.tensor([0], device=query.device)
         i = 0
+        resid = None      # alias of `query` for the next fused block's residual connection (see _fused_norm)
         while i < len(order):
             op = order[i]
             fuse = (not self.pre_norm) and i + 1 < len(order) and order[i + 1] == "norm" and query.is_cuda
+            # the norm closing this block feeds another block + its residual: ask for the alias pair
+            twin = (fuse and i + 2 < len(order) and order[i + 2] in ("cross_attn", "ffn")
+                    and torch.is_grad_enabled())
+            res_in, resid = (query if resid is None else resid), None
             if op == "self_attn":
                 att = self.attentions[ai]
                 if fuse and isinstance(att, TemporalSelfAttention) and att.batch_first:
@@ -275,7 +286,9 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                                      bev_hw=None if bev_h is None else (bev_h, bev_w),
                                      value_pre=kwargs.get("tsa_value_pre"),
                                      prev_no_grad=bool(kwargs.get("tsa_prev_no_grad", False)))
-                    query = _fused_norm(self.norms[ni], pre, query, att.dropout)
+                    query = _fused_norm(self.norms[ni], pre, res_in, att.dropout, twin=twin)
+                    if twin:
+                        query, resid = query
                     ni += 1
                     i += 1
                 else:
@@ -292,7 +305,9 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                                      kwargs.get("bev_mask"), spatial_shapes, level_start_index,
                                      kwargs.get("sca_plan"), kwargs.get("level_hw_host"),
                                      kwargs.get("sca_value_pre"))
-                    query = _fused_norm(self.norms[ni], pre, query, att.dropout)
+                    query = _fused_norm(self.norms[ni], pre, res_in, att.dropout, twin=twin)
+                    if twin:
+                        query, resid = query
                     ni += 1
                     i += 1
                 else:
@@ -310,10 +325,13 @@ class BEVFormerLayer(MyCustomBaseTransformerLayer):
                         and isinstance(ffn.dropout_layer, nn.Identity)):
                     emit = (carry is not None and carry.get("emit") and i + 2 == len(order)
                             and bev_pos is not None and bev_pos.dtype == query.dtype)
-                    out = _fused_norm(self.norms[ni], ffn.transform(query), query,
-                                      ffn.layers[ffn.num_fcs], bev_pos if emit else None)
+                    out = _fused_norm(self.norms[ni], ffn.transform(query), res_in,
+                                      ffn.layers[ffn.num_fcs], bev_pos if emit else None,
+                                      twin=twin and not emit)
                     if emit:
                         query, carry["q_in"] = out
+                    elif twin:
+                        query, resid = out
                     else:
                         query = out
                     ni += 1

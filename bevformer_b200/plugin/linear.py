@@ -25,6 +25,16 @@ def _use_tc(x: torch.Tensor, weight: torch.Tensor) -> bool:
             and weight.shape[0] % 16 == 0 and os.environ.get("BEVF_GEMM", "tc") != "cublas")
 
 
+def stacked_head(weights, biases, x):
+    """(W, b) of several Linear layers applied as one projection (sampling_offsets | attention_weights).
+    On the tcgen05 path with a gradient arena the stack is a view of the arena's parameter buffer."""
+    from ..arena import stacked
+    n, k = sum(w.shape[0] for w in weights), weights[0].shape[1]
+    direct = (x.is_cuda and x.dtype == torch.bfloat16 and k % 64 == 0 and n % 16 == 0
+              and os.environ.get("BEVF_GEMM", "tc") != "cublas")
+    return stacked(weights, direct), stacked(biases, direct)
+
+
 def _arena_ctx(weight, bias):
     """(arena, accumulators, params) when weight (and bias) accumulate in a gradient arena, else None."""
     ar, accs = arena_of(weight, bias) if bias is not None else arena_of(weight)
@@ -161,6 +171,9 @@ class _SharedInputProjections(Function):
             xc.record_stream(aux)
         state["ready"] = ready
         ctx.save_for_backward(xc, *ws)
+        # an output whose gradient was handed over through the early path arrives as None: keep it None
+        # (the default would materialise a zero tensor the size of the value maps for each of them)
+        ctx.set_materialize_grads(False)
         ctx.meta = meta
         ctx.arenas = [_arena_ctx(wb[i], wb[i + 1]) for i in range(0, len(wb), 2)]
         ctx.state = state

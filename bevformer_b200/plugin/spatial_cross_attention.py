@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import linear, sca_sampling_head
+from .linear import linear, sca_sampling_head, stacked_head
 from .registry import ATTENTION, _register, build_attention
 from .temporal_self_attention import _check_head_dim, ring_offsets_
 
@@ -133,12 +133,11 @@ class MSDeformableAttention3D(nn.Module):
         nn.init.zeros_(self.value_proj.bias)
         self._is_init = True
 
-    def head_weights(self):
-        """sampling_offsets and attention_weights stacked into one projection."""
-        from ..arena import stacked
+    def head_weights(self, x):
+        """sampling_offsets and attention_weights stacked into one projection (applied to ``x``)."""
         ws, bs_ = (self.sampling_offsets.weight, self.attention_weights.weight), \
                   (self.sampling_offsets.bias, self.attention_weights.bias)
-        return stacked(ws, torch.cat(ws, 0)), stacked(bs_, torch.cat(bs_, 0))
+        return stacked_head(ws, bs_, x)
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
@@ -163,7 +162,7 @@ class MSDeformableAttention3D(nn.Module):
         if key_padding_mask is not None:
             v = v.masked_fill(key_padding_mask[..., None], 0.0)
         v = v.view(bs, nv, m, -1)
-        w, b = self.head_weights()
+        w, b = self.head_weights(query)
         ss = torch.as_tensor(spatial_shapes).to(device=query.device, dtype=torch.int64)
         lsi = torch.as_tensor(level_start_index).to(device=query.device, dtype=torch.int64)
         d = reference_points.shape[2]
@@ -223,7 +222,7 @@ class SpatialCrossAttention(nn.Module):
         if int(s) <= 0 or p % d != 0:
             raise AssertionError("num_points must be a multiple of the pillar anchors")   # :369
         # offsets / logits once per BEV query: they do not depend on the camera (:338-341)
-        w, b = da.head_weights()
+        w, b = da.head_weights(query)
         loc, attn = sca_sampling_head(query, w, b, plan.ref_cam, plan.pair_q, plan.pair_cam,
                                       plan.pair_of, ss, bs, nq, m, l, p)
         # value_proj over every camera's feature pyramid (:334), batch-major like the reference

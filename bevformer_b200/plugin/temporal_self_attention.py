@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .linear import linear, linear_fp32_out, tsa_sampling_head
+from .linear import linear, linear_fp32_out, stacked_head, tsa_sampling_head
 from .registry import ATTENTION, _register
 
 
@@ -109,10 +109,9 @@ class TemporalSelfAttention(nn.Module):
         v = v.reshape(bs * 2, nv, self.num_heads, -1)
         if early is not None and key_padding_mask is None:
             v._bevf_early = early
-        from ..arena import stacked
         ws, bs_ = (self.sampling_offsets.weight, self.attention_weights.weight), \
                   (self.sampling_offsets.bias, self.attention_weights.bias)
-        w, b = stacked(ws, torch.cat(ws, 0)), stacked(bs_, torch.cat(bs_, 0))
+        w, b = stacked_head(ws, bs_, q_cat)
 
         ss = torch.as_tensor(spatial_shapes).to(device=query.device, dtype=torch.int64)
         lsi = torch.as_tensor(level_start_index).to(device=query.device, dtype=torch.int64)

@@ -107,6 +107,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--profile", action="store_true", help="launch each kernel once (for ncu)")
+    ap.add_argument("--kernels", action="store_true", help="also print per-kernel durations of the backward")
     args = ap.parse_args()
     dev = "cuda"
     w = syn.WORKLOADS["base"]
@@ -188,6 +189,18 @@ def main():
             sz = 4 if dt == torch.float32 else 2
             t_f, t_fmin = time_op(fwd, args.iters, flush)
             t_b, t_bmin = time_op(bwd, args.iters, flush)
+            if args.kernels:                       # per-kernel durations of the backward (CUPTI records)
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    for _ in range(5):
+                        flush.zero_(); bwd()
+                    torch.cuda.synchronize()
+                agg = {}
+                for ev in prof.events():
+                    if ev.device_type == torch.autograd.DeviceType.CUDA and "msda" in ev.name:
+                        agg.setdefault(ev.name[:70], []).append(ev.device_time)
+                for k, ts in agg.items():
+                    print(f"    {name} {str(dt).split('.')[-1]:9s} {sum(ts) / len(ts):8.1f} us x{len(ts) // 5}  {k}", flush=True)
             C = M * 32
             bf = B * S * C * sz + nrows * M * L * P * 12 + nrows * C * sz
             bb = bf + B * S * C * 4 + nrows * M * L * P * 12

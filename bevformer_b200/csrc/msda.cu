@@ -23,6 +23,7 @@
 //     finishes grad_loc / grad_attn.  grad_value is scattered with 16 B vector reductions
 //     (REDG.E.ADD.F32x4), never scalar atomics.
 #include <cstdlib>
+#include <cstring>
 
 #include "msda_common.cuh"
 
@@ -129,13 +130,18 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const float *__restrict__ attn, const TG *__restrict__ grad_out,
              float *__restrict__ grad_value, float *__restrict__ grad_loc,
              float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M, int Q,
-             int L, int P, int magic, int iters, long long rows, unsigned red_skip) {
+             int L, int P, int magic, int iters, long long rows, unsigned red_skip,
+             const __grid_constant__ HostLevels host_levels) {
     // red_skip: bit l set = the grad_value contributions of level l are NOT scattered here (hybrid mode: the
     // coarse levels go through msda_bwd_splat_d32, which merges them in registers, on a second stream)
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
     constexpr bool kHalfDot = (VEC == 8) && (sizeof(TG) == 2);
     __shared__ LevelTab tab;
+    __shared__ unsigned s_skip;
+    if (threadIdx.x == 0)     // levels masked for the dense path only if that kernel saw the same pyramid
+        s_skip = (red_skip && host_levels.h[0] > 0 && !host_levels_match(host_levels, level_hw, level_start, L)) ? 0u : red_skip;
     load_level_tab(level_hw, level_start, L, M * 32, tab);
+    red_skip = s_skip;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
@@ -473,6 +479,11 @@ static unsigned splat_direct_mask() {
     return (unsigned)v;
 }
 
+int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t *ls_dev, const int32_t *hw_host,
+                          const float *loc, const float *attn, const void *grad_out, float *grad_value,
+                          const int32_t *map_range, int NB, int S, int M, int L, int P, cudaStream_t st,
+                          unsigned *handled, HostLevels *host_levels);                 // msda_dense.cu
+
 // second stream + events for the hybrid backward (created by bevf_msda_set_backward_mode(2), i.e. outside any
 // stream capture; the fork / join below is capturable)
 static cudaStream_t g_side_stream = nullptr;
@@ -518,13 +529,17 @@ template <typename T, typename TG>
 static int launch_bwd(const char *who, const void *value, const int64_t *hw, const int64_t *ls,
                       const float *loc, const float *attn, const void *go, float *gv, float *gl,
                       float *ga, const int *row_map, const int *order, int S, int M, int D, int Q,
-                      int L, int P, long long rows, cudaStream_t st) {
+                      int L, int P, long long rows, cudaStream_t st, unsigned done_levels = 0,
+                      const HostLevels *host_levels = nullptr) {
+    HostLevels hl;
+    if (host_levels) hl = *host_levels; else memset(&hl, 0, sizeof(hl));
+    // done_levels: grad_value of these levels is produced elsewhere (dense tensor-core path, msda_dense.cu)
     if (D == 32) {
         constexpr int G = Vec<T>::N;
         const int iters = pick_iters(rows, G);
         const long long per_block = (long long)(kThreads / 32) * G * iters;
         const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
-        const int mode = bwd_split_enabled();
+        const int mode = done_levels ? 0 : bwd_split_enabled();
         const bool can_split = M <= kSplatMaxHeads && S * (long long)M * 32 < (1ll << 31);
         if (mode == 1 && can_split) {
             if (int e = launch_splat<TG>(who, loc, attn, go, gv, row_map, order, hw, ls, S, M, Q, L, P,
@@ -532,7 +547,7 @@ static int launch_bwd(const char *who, const void *value, const int64_t *hw, con
                 return e;
             msda_bwd_d32<T, TG, false><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
                                                                   (const TG *)go, gv, gl, ga, row_map, S, M,
-                                                                  Q, L, P, (65536 + P - 1) / P, iters, rows, 0u);
+                                                                  Q, L, P, (65536 + P - 1) / P, iters, rows, 0u, hl);
         } else if (mode == 2 && can_split && L >= 2 && g_side_stream) {
             // hybrid: the coarse half of the pyramid (most collisions, 47 % of the reduction bytes at base)
             // through the register-merging splat on the second stream, everything else in the one-kernel
@@ -549,12 +564,12 @@ static int launch_bwd(const char *who, const void *value, const int64_t *hw, con
             cudaEventRecord(join, g_side_stream);
             msda_bwd_d32<T, TG, true><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
                                                                  (const TG *)go, gv, gl, ga, row_map, S, M,
-                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows, coarse);
+                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows, coarse, hl);
             cudaStreamWaitEvent(st, join, 0);
         } else {
             msda_bwd_d32<T, TG, true><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn,
                                                                  (const TG *)go, gv, gl, ga, row_map, S, M,
-                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows, 0u);
+                                                                 Q, L, P, (65536 + P - 1) / P, iters, rows, done_levels, hl);
         }
     } else {
         const unsigned grid = (unsigned)((rows + kThreads / 32 - 1) / (kThreads / 32));
@@ -591,7 +606,8 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
                               const float *attn, const void *grad_out, int grad_out_dtype,
                               float *grad_value, float *grad_loc, float *grad_attn,
                               const int *row_map, const int *order, int B, int S, int M, int D, int Q,
-                              int L, int P, void *stream) {
+                              int L, int P, void *stream, unsigned done_levels = 0,
+                              const HostLevels *host_levels = nullptr) {
     if (int e = check_dims(who, B, S, M, D, Q, L, P)) return e;
     const long long rows = (row_map ? 1ll : (long long)B) * Q * M;
     if (rows == 0) return 0;
@@ -605,9 +621,9 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
     const bool vb = value_dtype == BEVF_DTYPE_BF16, gb = grad_out_dtype == BEVF_DTYPE_BF16;
     if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (grad_out_dtype != BEVF_DTYPE_F32 && !gb))
         return fail("%s: unsupported dtype code", who);
-    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st);
-    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st);
-    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st);
+    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels);
+    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels);
+    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels);
     return fail("%s: fp32 value with bf16 grad_out is not supported", who);
 }
 
@@ -653,6 +669,84 @@ extern "C" int bevf_msda_rows_backward(const void *value, int value_dtype, const
     return msda_backward_impl("bevf_msda_rows_backward", value, value_dtype, level_hw, level_start,
                               loc, attn, grad_out, grad_out_dtype, grad_value, grad_loc, grad_attn,
                               row_map, nullptr, B, S, M, D, R, L, P, stream);
+}
+
+// grad_value of the coarse levels through the dense tensor-core kernel (msda_dense.cu), everything else
+// (grad_loc, grad_attn, grad_value of the fine levels) through the one-kernel backward with those levels masked.
+// mode 1: both on the caller's stream; mode 2: the dense kernel on the library's second stream (fork / join
+// with events, capturable) -- it works out of shared memory and TMEM while the other is bound by L2 reductions.
+static std::atomic<int> g_dense_mode{-1};
+static int dense_mode() {
+    int v = g_dense_mode.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("BEVF_MSDA_DENSE");
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 1) v = 1;                      // (mode 2 needs its stream: only through the setter)
+        g_dense_mode.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+static int ensure_side_stream(const char *who) {
+    if (g_side_stream) return 0;
+    if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        g_side_stream = nullptr;
+        return fail("%s: cannot create the second stream", who);
+    }
+    for (int i = 0; i < kSideEvents; ++i) cudaEventCreateWithFlags(&g_side_events[i], cudaEventDisableTiming);
+    return 0;
+}
+
+extern "C" int bevf_msda_set_dense_backward(int mode) {
+    if (mode < 0 || mode > 2)
+        return fail("%s: mode must be 0 (off), 1 (same stream) or 2 (second stream)", "bevf_msda_set_dense_backward");
+    if (mode == 2)
+        if (int e = ensure_side_stream("bevf_msda_set_dense_backward")) return e;
+    g_dense_mode.store(mode, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int bevf_msda_rows_backward_dense(const void *value, int value_dtype, const int64_t *level_hw,
+                                             const int64_t *level_start, const int32_t *level_hw_host,
+                                             const float *loc, const float *attn, const void *grad_out,
+                                             int grad_out_dtype, float *grad_value, float *grad_loc,
+                                             float *grad_attn, const int32_t *row_map, const int32_t *map_range,
+                                             int B, int S, int M, int D, int R, int L, int P, void *stream) {
+    const char *who = "bevf_msda_rows_backward_dense";
+    if (!row_map && R > 0) return fail("%s: row_map is null", who);
+    if (int e = check_dims(who, B, S, M, D, R, L, P)) return e;
+    if (R == 0) return 0;
+    if (!level_hw_host || !map_range || !level_hw || !level_start || !loc || !attn || !grad_out || !grad_value)
+        return fail("%s: null pointer argument", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned handled = 0;
+    HostLevels hl;
+    memset(&hl, 0, sizeof(hl));
+    const int mode = dense_mode();
+    cudaEvent_t join = nullptr;
+    if (mode != 0 && D == 32 && grad_out_dtype == BEVF_DTYPE_BF16 && aligned16(loc) && aligned16(attn) &&
+        aligned16(grad_out) && aligned16(grad_value)) {
+        cudaStream_t ds = st;
+        if (mode == 2 && g_side_stream) {
+            cudaEvent_t fork = g_side_events[g_side_ev_next.fetch_add(1) % kSideEvents];
+            join = g_side_events[g_side_ev_next.fetch_add(1) % kSideEvents];
+            cudaEventRecord(fork, st);
+            cudaStreamWaitEvent(g_side_stream, fork, 0);
+            ds = g_side_stream;
+        }
+        const int e = dense_coarse_backward(who, level_hw, level_start, level_hw_host, loc, attn, grad_out, grad_value,
+                                            map_range, B, S, M, L, P, ds, &handled, &hl);
+        if (join) cudaEventRecord(join, g_side_stream);
+        if (e) {
+            if (join) cudaStreamWaitEvent(st, join, 0);
+            return e;
+        }
+    }
+    const int e = msda_backward_impl(who, value, value_dtype, level_hw, level_start, loc, attn, grad_out,
+                                     grad_out_dtype, grad_value, grad_loc, grad_attn, row_map, nullptr, B, S, M, D,
+                                     R, L, P, stream, handled, &hl);
+    if (join) cudaStreamWaitEvent(st, join, 0);
+    return e;
 }
 
 extern "C" int bevf_msda_set_backward_mode(int mode) {

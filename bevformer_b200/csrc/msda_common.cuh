@@ -77,6 +77,21 @@ __device__ __forceinline__ void load_level_tab(const int64_t *level_hw, const in
     __syncthreads();
 }
 
+// The pyramid as the HOST planned with it (dense tensor-core backward, msda_dense.cu).  Both kernels of that path
+// evaluate the same predicate on the device -- host shapes == device spatial_shapes / level_start -- so a stale
+// host copy degrades to the plain reduction path instead of producing a wrong gradient.
+struct HostLevels {
+    int h[kMaxLevels], w[kMaxLevels], start[kMaxLevels];
+};
+__device__ __forceinline__ bool host_levels_match(const HostLevels &hl, const int64_t *level_hw,
+                                                  const int64_t *level_start, int L) {
+    bool ok = true;
+    for (int l = 0; l < L; ++l)
+        ok = ok && (int)level_hw[2 * l] == hl.h[l] && (int)level_hw[2 * l + 1] == hl.w[l] &&
+             (int)level_start[l] == hl.start[l];
+    return ok;
+}
+
 // ---- per-storage-type math ---------------------------------------------------------------------
 __device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
     float d;

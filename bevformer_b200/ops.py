@@ -250,9 +250,11 @@ def msda_rows_forward_staged(value, spatial_shapes, level_start_index, level_hw_
 
 
 def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
-                       grad_value=None, group_order=None):
+                       grad_value=None, group_order=None, dense=None):
     """``group_order`` (R,) int32: optional permutation of the rows in which runs of 64 entries are
-    spatial neighbours on one value map (see bevf_msda_rows_backward_ordered)."""
+    spatial neighbours on one value map (see bevf_msda_rows_backward_ordered).
+    ``dense`` = (level_hw_host, map_range) for row lists grouped by value map: grad_value of the coarse levels
+    through the tensor-core kernel (bevf_msda_rows_backward_dense)."""
     for t, n in ((value, "value"), (loc, "sampling_loc"), (attn, "attn_weight"),
                  (row_map, "row_map"), (grad_output, "grad_output")):
         _need_cuda(t, n)
@@ -268,6 +270,21 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
         if group_order is not None and (group_order.dtype != torch.int32 or group_order.numel() != R
                                         or not group_order.is_cuda):
             raise RuntimeError("group_order must be a CUDA int32 tensor with one entry per row")
+        if dense is not None and group_order is None:
+            import ctypes
+            level_hw_host, map_range = dense
+            _need_cuda(map_range, "map_range")
+            if len(level_hw_host) != L or map_range.numel() != 2 * NB or map_range.dtype != torch.int32:
+                raise RuntimeError("dense backward: level_hw_host / map_range do not match value and sampling_loc")
+            hw = (ctypes.c_int32 * (2 * L))(*[int(v) for hw_ in level_hw_host for v in hw_])
+            st = lib.bevf_msda_rows_backward_dense(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                                   ctypes.addressof(hw), loc.data_ptr(), attn.data_ptr(),
+                                                   grad_output.data_ptr(), _DT[grad_output.dtype],
+                                                   grad_value.data_ptr(), grad_loc.data_ptr(),
+                                                   grad_attn.data_ptr(), row_map.data_ptr(), map_range.data_ptr(),
+                                                   NB, S, M, D, R, L, P, _stream_ptr(value))
+            _lib.check(st, lib)
+            return grad_value, grad_loc, grad_attn
         st = lib.bevf_msda_rows_backward_ordered(value.data_ptr(), _DT[value.dtype], ss.data_ptr(),
                                                  ls.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                                                  grad_output.data_ptr(), _DT[grad_output.dtype],
@@ -304,6 +321,7 @@ class SamplerRows(Function):
             out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         ctx.group_order = group_order
+        ctx.dense = staged if (staged is not None and value.shape[-1] == 32) else None
         ctx.value_early = getattr(value, "_bevf_early", None)     # see plugin/linear.py::shared_input_projections
         ctx.gv_zero = None
         aux = aux_stream(value.device)
@@ -333,7 +351,7 @@ class SamplerRows(Function):
             gv0, done = ctx.gv_zero
             torch.cuda.current_stream(value.device).wait_event(done)
         gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
-                                        group_order=ctx.group_order)
+                                        group_order=ctx.group_order, dense=ctx.dense)
         if ctx.value_early is not None and ctx.value_early(gv):
             # the producer of `value` took the fp32 gradient (conversion + its GEMMs run off the critical path)
             return None, gl, ga, None, None, None, None, None

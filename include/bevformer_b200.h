@@ -157,6 +157,32 @@ BEVF_API int bevf_msda_rows_forward_staged(const void *value, int value_dtype, c
                                            int L, int P, void *stream);
 
 /*
+ * bevf_msda_rows_backward for row lists grouped by value map (the SCA pair list), with grad_value of the
+ * COARSE pyramid levels computed as a dense product on the tensor cores (csrc/msda_dense.cu) instead of one
+ * L2 reduction per (sample, corner): for a (value map, head) the col2im scatter of
+ * multi_scale_deformable_attn_function.py:150-160 is  C[pixel, row] x grad_out[row, 32]  with a sparse
+ * coefficient matrix C (attention weight x bilinear weight, rounded to bf16); bins of <= 2048 pixels keep
+ * their fp32 accumulators in TMEM, the coefficients of 16 rows at a time are written into shared memory by
+ * one thread per (row, level) and multiplied with tcgen05.mma.  Levels with more than BEVF_DENSE_MAXPIX
+ * pixels (default 8192), grad_loc and grad_attn come from the one-kernel backward as before.
+ * Used when grad_out is bf16 and head_dim is 32 with 4 or 8 points per level; any other configuration
+ * runs exactly bevf_msda_rows_backward.  grad_value must be zero-filled or hold a running sum, as there.
+ *   level_hw_host  (L, 2) int32 HOST copy of level_hw (the bins are planned on the host; a device-side
+ *                  mismatch is a caller bug and traps)
+ *   map_range      (B, 2) int32 DEVICE: [first, end) rows of every value map (bevf_sca_plan_build)
+ * bevf_msda_set_dense_backward: 0 = never use the dense kernel, 1 = on the caller's stream (default, or the
+ * environment variable BEVF_MSDA_DENSE), 2 = on a library-owned second stream next to the reduction kernel
+ * (fork / join with events, capturable).
+ */
+BEVF_API int bevf_msda_rows_backward_dense(const void *value, int value_dtype, const int64_t *level_hw,
+                                           const int64_t *level_start, const int32_t *level_hw_host,
+                                           const float *loc, const float *attn, const void *grad_out,
+                                           int grad_out_dtype, float *grad_value, float *grad_loc,
+                                           float *grad_attn, const int32_t *row_map, const int32_t *map_range,
+                                           int B, int S, int M, int D, int R, int L, int P, void *stream);
+BEVF_API int bevf_msda_set_dense_backward(int mode);
+
+/*
  * Selects how bevf_msda_*backward* computes grad_value (process-wide; default 0, or the environment
  * variable BEVF_MSDA_BWD=split).  0: one kernel, one 16 B-vector L2 reduction per corner contribution.
  * 1: gather kernel + a splat kernel that merges the contributions of 64 neighbouring rows in registers

@@ -180,8 +180,15 @@ def main():
             out = fwd()
             g = torch.randn_like(out)
             gv = torch.zeros(v.shape, device=dev, dtype=torch.float32)
+            dense = None
+            if name == "sca_rig" and dt == torch.bfloat16 and os.environ.get("BENCH_DENSE", "0") != "0":
+                from bevformer_b200 import _lib
+                assert _lib.load().bevf_msda_set_dense_backward(int(os.environ["BENCH_DENSE"])) == 0
+                per_cam = torch.bincount(row_map[row_map >= 0].long(), minlength=B)
+                ends = per_cam.cumsum(0)
+                dense = (list(w.levels), torch.stack([ends - per_cam, ends], 1).to(torch.int32).contiguous())
             if row_map is not None:
-                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order)
+                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order, dense=dense)
             else:
                 bwd = lambda: ops.msda_backward(vd, ss, lsi, loc, attn, g, gv)
             if args.profile:
@@ -204,7 +211,7 @@ def main():
             C = M * 32
             bf = B * S * C * sz + nrows * M * L * P * 12 + nrows * C * sz
             bb = bf + B * S * C * 4 + nrows * M * L * P * 12
-            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], bwd_mode=os.environ.get("BEVF_MSDA_BWD", "split"),
+            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], bwd_mode=os.environ.get("BEVF_MSDA_BWD", "one"), dense=os.environ.get("BENCH_DENSE", "0") if dense is not None else "0",
                      splat_direct=os.environ.get("BEVF_SPLAT_DIRECT", "0"), fwd_ms=round(t_f, 4),
                      bwd_ms=round(t_b, 4), fwd_alg_MB=round(bf / 1e6, 1), bwd_alg_MB=round(bb / 1e6, 1),
                      fwd_GBs=round(bf / t_f / 1e6, 1), bwd_GBs=round(bb / t_b / 1e6, 1),

@@ -763,22 +763,10 @@ static long dense_env(const char *name, long dflt) {
     return e ? strtol(e, nullptr, 0) : dflt;
 }
 
-// Plans the bins from the HOST copy of the pyramid and launches the dense kernel for every level with at most
-// `BEVF_DENSE_MAXPIX` pixels.  *handled = mask of the levels whose grad_value it produced (0: not applicable --
-// the caller then leaves every level to the reduction path).
-int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t *ls_dev, const int32_t *hw_host,
-                          const float *loc, const float *attn, const void *grad_out, float *grad_value,
-                          const int32_t *map_range, int NB, int S, int M, int L, int P, cudaStream_t st,
-                          unsigned *handled, HostLevels *host_levels) {
-    *handled = 0;
-    static const long max_pix = dense_env("BEVF_DENSE_MAXPIX", 8192);
-    static const long tiles = dense_env("BEVF_DENSE_TILES", 16);
-    static const long chunk = dense_env("BEVF_DENSE_CHUNK", 512);
-    if ((P != 4 && P != 8) || L > kMaxLevels || NB <= 0 || max_pix <= 0) return 0;
-    if (tiles != 8 && tiles != 16) return fail("%s: BEVF_DENSE_TILES must be 8 or 16", who);
-    if (chunk < kDnK || chunk % kDnK) return fail("%s: BEVF_DENSE_CHUNK must be a positive multiple of 16", who);
-    const int cap = (int)tiles * 128;
-    DenseBins bins;
+// Bins of at most `cap` consecutive pixels over the levels with at most `max_pix` pixels: a level larger than a bin
+// is cut into ceil(n / cap) bins, consecutive small levels share one (the kernel gives each level of a bin its own
+// group of scatter threads).  Returns the mask of the covered levels, -1 for a bad shape, -2 if the table overflows.
+static int plan_dense_bins(const int32_t *hw_host, int L, long max_pix, int cap, DenseBins &bins, long long *total) {
     memset(&bins, 0, sizeof(bins));
     bins.L = L;
     long long start = 0;
@@ -786,7 +774,7 @@ int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t 
     int open = -1;                                       // bin that may still take the next level
     for (int l = 0; l < L; ++l) {
         const int h = hw_host[2 * l], w = hw_host[2 * l + 1];
-        if (h <= 0 || w <= 0 || h >= 32768 || w >= 32768) return fail("%s: bad host level shape", who);
+        if (h <= 0 || w <= 0 || h >= 32768 || w >= 32768) return -1;
         const long long n = (long long)h * w;
         bins.hl.h[l] = h; bins.hl.w[l] = w; bins.hl.start[l] = (int)start;
         if (n <= max_pix) {
@@ -795,7 +783,7 @@ int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t 
                 bins.n[open] += (int)n;
             } else {
                 const int parts = (int)((n + cap - 1) / cap);
-                if (bins.nbins + parts > kDnMaxBins) return 0;          // pyramid too large for the table
+                if (bins.nbins + parts > kDnMaxBins) return -2;
                 long long off = 0;
                 for (int i = 0; i < parts; ++i) {
                     const int bi = bins.nbins++;
@@ -813,6 +801,31 @@ int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t 
         }
         start += n;
     }
+    *total = start;
+    return (int)mask;
+}
+
+// Plans the bins from the HOST copy of the pyramid and launches the dense kernel for every level with at most
+// `BEVF_DENSE_MAXPIX` pixels.  *handled = mask of the levels whose grad_value it produced (0: not applicable --
+// the caller then leaves every level to the reduction path).
+int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t *ls_dev, const int32_t *hw_host,
+                          const float *loc, const float *attn, const void *grad_out, float *grad_value,
+                          const int32_t *map_range, int NB, int S, int M, int L, int P, cudaStream_t st,
+                          unsigned *handled, HostLevels *host_levels) {
+    *handled = 0;
+    static const long max_pix = dense_env("BEVF_DENSE_MAXPIX", 8192);
+    static const long tiles = dense_env("BEVF_DENSE_TILES", 16);
+    static const long chunk = dense_env("BEVF_DENSE_CHUNK", 512);
+    if ((P != 4 && P != 8) || L > kMaxLevels || NB <= 0 || max_pix <= 0) return 0;
+    if (tiles != 8 && tiles != 16) return fail("%s: BEVF_DENSE_TILES must be 8 or 16", who);
+    if (chunk < kDnK || chunk % kDnK) return fail("%s: BEVF_DENSE_CHUNK must be a positive multiple of 16", who);
+    const int cap = (int)tiles * 128;
+    DenseBins bins;
+    long long start = 0;
+    const int pm = plan_dense_bins(hw_host, L, max_pix, cap, bins, &start);
+    if (pm == -1) return fail("%s: bad host level shape", who);
+    if (pm == -2) return 0;                              // pyramid too large for the bin table
+    const unsigned mask = (unsigned)pm;
     if (start != S) return fail("%s: host level shapes do not add up to S (%lld vs %lld)", who, start, S);
     if (mask == 0) return 0;
     static int sms = 0;
@@ -868,3 +881,25 @@ int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t 
 }
 
 }  // namespace bevf
+
+// Host-only: the bin plan the dense backward would use for this pyramid (tests / diagnostics; no device work).
+extern "C" int bevf_msda_dense_plan(const int32_t *level_hw_host, int L, int max_pix, int tiles, int32_t *bins_out,
+                                    int bins_cap, uint32_t *level_mask) {
+    using namespace bevf;
+    const char *who = "bevf_msda_dense_plan";
+    if (!level_hw_host || !bins_out || !level_mask || L <= 0 || L > kMaxLevels || (tiles != 8 && tiles != 16))
+        return -fail("%s: bad argument", who);
+    DenseBins bins;
+    long long total = 0;
+    const int pm = plan_dense_bins(level_hw_host, L, max_pix, tiles * 128, bins, &total);
+    if (pm == -1) return -fail("%s: bad host level shape", who);
+    if (pm == -2) { *level_mask = 0; return 0; }
+    if (bins.nbins > bins_cap) return -fail("%s: output too small", who);
+    for (int i = 0; i < bins.nbins; ++i) {
+        int32_t *o = bins_out + i * (3 + kDnBinLevels);
+        o[0] = bins.s0[i]; o[1] = bins.n[i]; o[2] = bins.nlev[i];
+        for (int j = 0; j < kDnBinLevels; ++j) o[3 + j] = j < bins.nlev[i] ? bins.lev[i][j] : -1;
+    }
+    *level_mask = (unsigned)pm;
+    return bins.nbins;
+}

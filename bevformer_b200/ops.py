@@ -249,6 +249,18 @@ def msda_rows_forward_staged(value, spatial_shapes, level_start_index, level_hw_
     return out
 
 
+_DENSE_INIT = [False]
+
+
+def _dense_mode_init(lib) -> None:
+    """BEVF_MSDA_DENSE=2: the dense kernel on the library's second stream (created here, i.e. at the first eager
+    backward -- never inside a stream capture); 0 / 1 are read by the library itself."""
+    if not _DENSE_INIT[0]:
+        _DENSE_INIT[0] = True
+        if os.environ.get("BEVF_MSDA_DENSE", "") == "2" and not torch.cuda.is_current_stream_capturing():
+            _lib.check(lib.bevf_msda_set_dense_backward(2), lib)
+
+
 def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
                        grad_value=None, group_order=None, dense=None):
     """``group_order`` (R,) int32: optional permutation of the rows in which runs of 64 entries are
@@ -272,6 +284,7 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
             raise RuntimeError("group_order must be a CUDA int32 tensor with one entry per row")
         if dense is not None and group_order is None:
             import ctypes
+            _dense_mode_init(lib)
             level_hw_host, map_range = dense
             _need_cuda(map_range, "map_range")
             if len(level_hw_host) != L or map_range.numel() != 2 * NB or map_range.dtype != torch.int32:

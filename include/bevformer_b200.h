@@ -181,6 +181,14 @@ BEVF_API int bevf_msda_rows_backward_dense(const void *value, int value_dtype, c
                                            float *grad_attn, const int32_t *row_map, const int32_t *map_range,
                                            int B, int S, int M, int D, int R, int L, int P, void *stream);
 BEVF_API int bevf_msda_set_dense_backward(int mode);
+/*
+ * Host-only helper: the pixel bins bevf_msda_rows_backward_dense plans for a pyramid.  bins_out receives 7 int32
+ * per bin {first pixel, pixel count, number of levels, level ids (4, -1 padded)}; *level_mask the levels covered;
+ * returns the number of bins (0: nothing applies), negative on a bad argument.  tiles = 8 or 16 accumulator
+ * tiles of 128 pixels per bin.  No device work.
+ */
+BEVF_API int bevf_msda_dense_plan(const int32_t *level_hw_host, int L, int max_pix, int tiles, int32_t *bins_out,
+                                  int bins_cap, uint32_t *level_mask);
 
 /*
  * Selects how bevf_msda_*backward* computes grad_value (process-wide; default 0, or the environment

@@ -680,7 +680,7 @@ static int dense_mode() {
     int v = g_dense_mode.load(std::memory_order_relaxed);
     if (v < 0) {
         const char *e = getenv("BEVF_MSDA_DENSE");
-        v = e ? atoi(e) : 1;
+        v = e ? atoi(e) : 0;                            // default: off until the caller (or the environment) opts in
         if (v < 0 || v > 1) v = 1;                      // (mode 2 needs its stream: only through the setter)
         g_dense_mode.store(v, std::memory_order_relaxed);
     }

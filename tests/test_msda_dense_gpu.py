@@ -5,6 +5,8 @@ test files pin to Oracle-S and the golden vectors, on ragged row lists / split a
 points, and (b) Oracle-S itself on the real SCA launch of the headline benchmark.
 Bar: 1e-2 for bf16 storage (BASELINE.json north_star), max|err| / max(1, max|ref|); the coefficients of the
 dense path are rounded to bf16 (2^-9 relative, independent per term), accumulation is fp32."""
+import os
+
 import pytest
 import torch
 
@@ -14,6 +16,16 @@ from tests.util import fixed_projection, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def dense_on():
+    """The dense kernel is what these tests are about: switch it on explicitly (bevf_msda_set_dense_backward),
+    whatever the library default / environment says, and restore the previous setting afterwards."""
+    lib = _lib.load()
+    assert lib.bevf_msda_set_dense_backward(1) == 0
+    yield
+    lib.bevf_msda_set_dense_backward(int(os.environ.get("BEVF_MSDA_DENSE", "0") or 0))
 
 
 def _ragged_case(levels, rows_per_map, heads, pts, seed, gap=37):
@@ -111,7 +123,7 @@ def test_dense_backward_base_rig_against_oracle(mode):
         gvp, glp, gap = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout)
         torch.cuda.synchronize()
     finally:
-        lib.bevf_msda_set_dense_backward(1)
+        lib.bevf_msda_set_dense_backward(1)        # (the fixture restores the process default)
     assert torch.equal(gl, glp) and torch.equal(ga, gap)
     print("dense vs plain", rel_err(gv.cpu(), gvp.cpu()))
     if mode == 2:                   # the oracle comparison once is enough: same kernels, another stream

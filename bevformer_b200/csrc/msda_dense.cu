@@ -322,6 +322,13 @@ msda_bwd_dense_tc(const __grid_constant__ DenseBins bins, const int64_t *__restr
                     const float x = (p & 1) ? lq.z : lq.x, y = (p & 1) ? lq.w : lq.y;
                     const float a = (p & 3) == 0 ? aq.x : (p & 3) == 1 ? aq.y : (p & 3) == 2 ? aq.z : aq.w;
                     if (a == 0.f) continue;
+                    {   // cheap rejection first: a level cut into several bins is scanned once per bin, and most of
+                        // its samples fall into another one (same rounding as make_corner: unfused multiply / add)
+                        const float yy = __fadd_rn(__fmul_rn(y, (float)H), -0.5f);
+                        if (!(yy > -1.f) || !(yy < (float)H)) continue;
+                        const int y0 = (int)floorf(yy);
+                        if (lbase + (min(y0 + 1, H - 1) + 1) * W <= 0 || lbase + max(y0, 0) * W >= nb) continue;
+                    }
                     const Corner c = make_corner(x, y, H, W);
                     if (!c.valid) continue;
                     const int r00 = lbase + c.pidx, r01 = r00 + c.dx, r10 = r00 + c.dy * W, r11 = r10 + c.dx;

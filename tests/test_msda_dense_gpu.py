@@ -75,7 +75,8 @@ def test_dense_backward_equals_plain(case):
     gv0, gl0, ga0 = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout)
     gv1, gl1, ga1 = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout, dense=(c["levels"], rng))
     torch.cuda.synchronize()
-    assert torch.equal(gl0, gl1) and torch.equal(ga0, ga1)          # same kernel, same arithmetic
+    used = row_map >= 0                                             # unused rows are never written (torch.empty)
+    assert torch.equal(gl0[used], gl1[used]) and torch.equal(ga0[used], ga1[used])   # same kernel, same arithmetic
     err = rel_err(gv1.cpu(), gv0.cpu())
     lsl = lsi.tolist() + [int(v.shape[1])]
     per_level = [rel_err(gv1[:, lsl[i]:lsl[i + 1]].cpu(), gv0[:, lsl[i]:lsl[i + 1]].cpu()) for i in range(len(c["levels"]))]
@@ -124,7 +125,8 @@ def test_dense_backward_base_rig_against_oracle(mode):
         torch.cuda.synchronize()
     finally:
         lib.bevf_msda_set_dense_backward(1)        # (the fixture restores the process default)
-    assert torch.equal(gl, glp) and torch.equal(ga, gap)
+    used = row_map >= 0
+    assert torch.equal(gl[used], glp[used]) and torch.equal(ga[used], gap[used])
     print("dense vs plain", rel_err(gv.cpu(), gvp.cpu()))
     if mode == 2:                   # the oracle comparison once is enough: same kernels, another stream
         assert rel_err(gv.cpu(), gvp.cpu()) < 1e-2

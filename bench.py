@@ -216,6 +216,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
+    lib = _lib.load()
+    if args.dense is not None:
+        _lib.check(lib.bevf_msda_set_dense_backward(args.dense), lib)
+    elif os.environ.get("BEVF_MSDA_DENSE", "") == "2":
+        _lib.check(lib.bevf_msda_set_dense_backward(2), lib)
+    dense_mode = int(lib.bevf_msda_get_dense_backward())
     cfg = CONFIGS[args.config]
     w = syn.WORKLOADS[cfg["workload"]]
     dtype = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
@@ -494,14 +500,22 @@ def run_ours(args):
     roof = None
     if t_bwd and args.config == "base":
         ab = sca_alg_bytes(w, pairs, True)
-        roof = {"bound": "hbm", "kernel": "msda_bwd_d32<bf16,bf16> (SCA sampler backward)",
+        kname = "msda_bwd_d32<bf16,bf16> (SCA sampler backward)"
+        if dense_mode:
+            kname = ("SCA sampler backward = msda_bwd_dense_tc (grad_value of levels 1-3: coefficient scatter into UMMA slabs + "
+                     "tcgen05.mma into TMEM bins" + (", on the library's second stream" if dense_mode == 2 else "") +
+                     ") + msda_bwd_d32<bf16,bf16> (grad_loc, grad_attn, level-0 reductions); timed as one op")
+        roof = {"bound": "hbm", "kernel": kname,
                 "achieved": ab / t_bwd / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": ab / t_bwd / 1e6 / peak, "peak_source": peak_src,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
                 # `ncu --set full` capture named in traffic_source (ncu cannot run inside a bench run)
                 "traffic": 396693504 + 245205504,
-                "traffic_source": "profiles/r1p_ncu_full_msda_bwd_raw.csv (msda_bwd_d32<bf16,bf16>, SCA real geometry; "
-                                  "the kernel is unchanged since that capture)",
+                "traffic_source": "profiles/r1p_ncu_full_msda_bwd_raw.csv (msda_bwd_d32<bf16,bf16> with every level on the "
+                                  "reduction path, SCA real geometry)" + (
+                                      "; the dense path moves the same compulsory bytes (value, grad_out, loc/attn read twice: "
+                                      "+137 MB)" if dense_mode else ""),
+                "dense_backward_mode": dense_mode,
                 "in_view_pairs": pairs,
                 "alg_bytes_per_launch": ab, "avg_launch_ms": t_bwd,
                 "launches_timed": len(kt["msda_rows_backward"]), "timing": timer_note,
@@ -586,6 +600,10 @@ def main():
     ap.add_argument("--config", default="base", choices=sorted(CONFIGS),
                     help="BASELINE.json config to run (default: base = the headline metric)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a CUDA graph")
+    ap.add_argument("--dense", type=int, default=None, choices=[0, 1, 2],
+                    help="SCA sampler backward: 0 = every level on the L2-reduction kernel, 1 = coarse levels through the "
+                         "tensor-core kernel (csrc/msda_dense.cu) on the same stream, 2 = on the library's second stream "
+                         "(default: the library's setting / BEVF_MSDA_DENSE)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

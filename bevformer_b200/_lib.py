@@ -38,6 +38,7 @@ SIGNATURES = {
                                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
                                       + [c_int] * 7 + [c_void_p]),
     "bevf_msda_set_dense_backward": (c_int, [c_int]),
+    "bevf_msda_get_dense_backward": (c_int, []),
     "bevf_msda_dense_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "bevf_sca_plan_workspace_ints": (c_int64, [c_int, c_int]),
     "bevf_sca_plan_build": (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_void_p]),

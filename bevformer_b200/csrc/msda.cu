@@ -706,6 +706,8 @@ extern "C" int bevf_msda_set_dense_backward(int mode) {
     return 0;
 }
 
+extern "C" int bevf_msda_get_dense_backward(void) { return dense_mode(); }
+
 extern "C" int bevf_msda_rows_backward_dense(const void *value, int value_dtype, const int64_t *level_hw,
                                              const int64_t *level_start, const int32_t *level_hw_host,
                                              const float *loc, const float *attn, const void *grad_out,

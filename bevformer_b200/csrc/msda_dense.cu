@@ -137,6 +137,23 @@ __device__ __forceinline__ uint32_t slab_off(int row, int k) {
     return ((uint32_t)(row >> 6) << 11) + ((uint32_t)k << 7) + ((((uint32_t)(row >> 3) & 7u) ^ ((uint32_t)k & 7u)) << 4) +
            (((uint32_t)row & 7u) << 1);
 }
+// volatile global loads: they keep their place among the other volatile instructions (barrier waits, shared-memory
+// accesses), i.e. the prefetch of the next step really is issued before this step's work
+__device__ __forceinline__ float2 ldg_f2(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_f1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_u4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned short lds16(uint32_t addr) {
     unsigned short h;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr) : "memory");
@@ -293,15 +310,15 @@ msda_bwd_dense_tc(const __grid_constant__ DenseBins bins, const int64_t *__restr
                     q[i].x = q[i].y = q[i].a = 0.f;
                     if (live && on[i]) {
                         const long long e = (((long long)r * M + m) * L + lv[i]) * P + pt;
-                        const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + e);
-                        q[i].x = xy.x; q[i].y = xy.y; q[i].a = __ldg(attn + e);
+                        const float2 xy = dn::ldg_f2(reinterpret_cast<const float2 *>(loc) + e);
+                        q[i].x = xy.x; q[i].y = xy.y; q[i].a = dn::ldg_f1(attn + e);
                     }
                 }
             };
             auto load_gout = [&](int step) -> uint4 {
                 const int r = r_begin + step * kDnK + gk;
                 if (g_role && step < nsteps && r < r_end)
-                    return __ldg(reinterpret_cast<const uint4 *>(grad_out + ((long long)r * M + m) * 32 + gc * 8));
+                    return dn::ldg_u4(reinterpret_cast<const uint4 *>(grad_out + ((long long)r * M + m) * 32 + gc * 8));
                 return make_uint4(0, 0, 0, 0);
             };
             auto unscatter = [&]() {

@@ -181,6 +181,7 @@ BEVF_API int bevf_msda_rows_backward_dense(const void *value, int value_dtype, c
                                            float *grad_attn, const int32_t *row_map, const int32_t *map_range,
                                            int B, int S, int M, int D, int R, int L, int P, void *stream);
 BEVF_API int bevf_msda_set_dense_backward(int mode);
+BEVF_API int bevf_msda_get_dense_backward(void);
 /*
  * Host-only helper: the pixel bins bevf_msda_rows_backward_dense plans for a pyramid.  bins_out receives 7 int32
  * per bin {first pixel, pixel count, number of levels, level ids (4, -1 padded)}; *level_mask the levels covered;

@@ -31,6 +31,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "msda_common.cuh"
 
@@ -185,7 +186,7 @@ msda_bwd_dense_tc(const __grid_constant__ DenseBins bins, const int64_t *__restr
                   const int64_t *__restrict__ level_start, const float *__restrict__ loc,
                   const float *__restrict__ attn, const bf16 *__restrict__ grad_out,
                   float *__restrict__ grad_value, const int *__restrict__ map_range, int NB, int S, int M, int L,
-                  int chunk_rows) {
+                  int chunk_rows, int dbg) {
     static_assert(P == 4 || P == 8, "points per level: 4 or 8");
     static_assert(kTiles == 8 || kTiles == 16, "accumulator tiles per bin");
     static_assert(NT >= 1 && NT <= 6, "scatter teams");
@@ -419,7 +420,7 @@ msda_bwd_dense_tc(const __grid_constant__ DenseBins bins, const int64_t *__restr
                 // use after this one -- ordered before that use's atomicOr through full[] -> empty[]
                 if (tt == 0) s_dirty[2 * team + ((nuse + 1) & 1)] = 0;
                 unscatter();
-                uint32_t dirty = scatter(cur);
+                uint32_t dirty = (dbg & 2) ? 0u : scatter(cur);
                 dirty = __reduce_or_sync(0xffffffffu, dirty);
                 if (lane == 0 && dirty) atomicOr(&s_dirty[2 * team + (nuse & 1)], dirty);
                 if (g_role) fill_gout(gcur);
@@ -446,13 +447,14 @@ msda_bwd_dense_tc(const __grid_constant__ DenseBins bins, const int64_t *__restr
                     for (int i = 0; i < NT; ++i) if (i == t) { par = nfull[i] & 1u; nfull[i]++; }
                     dn::mbar_wait(&bar_full[t], par);
                     dn::tc_fence_after();
-                    const uint32_t mask = s_dirty[2 * t + par];      // the team clears it two uses later
+                    const uint32_t mask = (dbg & 8) ? (kTiles == 16 ? 0xffffu : 0xffu)
+                                                    : s_dirty[2 * t + par];      // the team clears it two uses later
                     const uint32_t mine = mask & (iw ? 0xaaaaaaaau : 0x55555555u);
                     const uint64_t da0 = dn::desc_mn_sw128(dn::s32(slab + t * kSlabBytes), 2048);
                     const uint64_t db = dn::desc_k_sw128(dn::s32(gtile + t * 4096));
 #pragma unroll
                     for (int i = 0; i < kTiles; ++i)
-                        if ((mine >> i) & 1u)
+                        if (((mine >> i) & 1u) && !(dbg & 1))
                             dn::umma_bf16(tmem_base + (uint32_t)(i * 32), da0 + (uint64_t)(i * (kDnTileBytes >> 4)), db, idesc,
                                           (udirty >> i) & 1u);
                     udirty |= mask;
@@ -469,7 +471,7 @@ msda_bwd_dense_tc(const __grid_constant__ DenseBins bins, const int64_t *__restr
         unit_phase ^= 1u;
         __syncthreads();
         // ---- flush: touched tiles -> grad_value (warps 0..3 = TMEM lane quarters)
-        const uint32_t touched = s_dirty[2 * NT];
+        const uint32_t touched = (dbg & (4 | 1)) ? 0u : s_dirty[2 * NT];
         if (warp < 4) {
             float *trw = tr + warp * (kDnTransposeBytes / 4);
 #pragma unroll 1
@@ -608,17 +610,26 @@ int dense_coarse_backward(const char *who, const int64_t *hw_dev, const int64_t 
     static const long teams_env = dense_env("BEVF_DENSE_TEAMS", 0);
     const int teams = teams_env > 0 ? (int)teams_env : (tiles == 16 ? 3 : 4);
     const size_t smem = 1024 + (size_t)teams * ((size_t)tiles * kDnTileBytes + 4096) + 4 * kDnTransposeBytes + 256;
+    static const long dbg = dense_env("BEVF_DENSE_DEBUG", 0);       // development: 1 = no MMAs, 2 = no scatter, 4 = no flush, 8 = every tile counts as touched
     auto launch = [&](auto kern) -> int {
-        static bool attr_done = false;                   // per instantiation of this generic lambda
-        if (!attr_done) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-                cudaGetLastError();
-                return fail("%s: cannot reserve shared memory for the dense backward", who);
+        // every instantiation has the same pointer type, so "configured" is remembered per kernel address
+        static const void *configured[16];
+        static int nconfigured = 0;
+        static std::mutex mu;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            bool seen = false;
+            for (int i = 0; i < nconfigured; ++i) seen = seen || configured[i] == (const void *)kern;
+            if (!seen) {
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail("%s: cannot reserve shared memory for the dense backward", who);
+                }
+                if (nconfigured < 16) configured[nconfigured++] = (const void *)kern;
             }
-            attr_done = true;
         }
         kern<<<(unsigned)sms, 128 * teams + 64, smem, st>>>(bins, hw_dev, ls_dev, loc, attn, (const bf16 *)grad_out,
-                                                           grad_value, map_range, NB, S, M, L, (int)chunk);
+                                                           grad_value, map_range, NB, S, M, L, (int)chunk, (int)dbg);
         return check_launch(who);
     };
     int e;

@@ -34,6 +34,9 @@ SIGNATURES = {
                                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p] + [c_int] * 7 + [c_void_p]),
     "bevf_msda_set_backward_mode": (c_int, [c_int]),
+    "bevf_msda_rows_backward_gv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7
+                                   + [c_void_p]),
     "bevf_msda_rows_backward_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
                                       + [c_int] * 7 + [c_void_p]),

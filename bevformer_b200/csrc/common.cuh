@@ -123,4 +123,10 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
                  :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// 16-byte bf16 vector reduction (8 channels): grad_value accumulated in bf16 (SASS: REDG.E.ADD.BF16x2.RN x4).
+__device__ __forceinline__ void red_add_v4_bf16x2(bf16 *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 }  // namespace bevf

@@ -123,12 +123,15 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
 // ------------------------------------------------------------------------------------------------
 // kScatter = false: the "gather" half only (grad_loc, grad_attn); grad_value then comes from
 // msda_bwd_splat_d32 (msda_splat.cuh), which merges the reductions of neighbouring rows in registers.
-template <typename T, typename TG, bool kScatter>
+// TV = storage type of grad_value: float (default: fp32 accumulation), or bf16 -- every contribution is then one
+// 16-byte bf16x2 vector reduction per lane (half the L2 reduction sectors, accumulation rounded to bf16 at every
+// add: for maps where a pixel collects few contributions, e.g. TemporalSelfAttention's single fine level).
+template <typename T, typename TG, bool kScatter, typename TV = float>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              const int64_t *__restrict__ level_start, const float *__restrict__ loc,
              const float *__restrict__ attn, const TG *__restrict__ grad_out,
-             float *__restrict__ grad_value, float *__restrict__ grad_loc,
+             TV *__restrict__ grad_value, float *__restrict__ grad_loc,
              float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M, int Q,
              int L, int P, int magic, int iters, long long rows, unsigned red_skip,
              const __grid_constant__ HostLevels host_levels) {
@@ -172,7 +175,9 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     // lanes write [16 + 4 sub, +4) -- and instruction B does the same for the high rows.  Each lane
     // therefore keeps 4 grad_out channels of its own row and 4 of its partner's, and reads the
     // partner's per-sample scalars with one extra shuffle each.
-    constexpr bool kPaired = (VEC == 8) && kScatter;
+    constexpr bool kGvHalf = sizeof(TV) == 2;
+    static_assert(!kGvHalf || VEC == 8, "bf16 grad_value needs bf16 value rows (8 channels per lane)");
+    constexpr bool kPaired = (VEC == 8) && kScatter && !kGvHalf;
     const bool hi = kPaired && (grp & 4);
     const long long vrow = voff - sub * VEC;                       // element offset of the row in its map
     long long vrow_a = vrow, vrow_b = vrow;
@@ -242,6 +247,17 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             // scatter w * a * g with 16 B reductions; zero-weight corners are skipped
             if constexpr (!kScatter) {
             } else if ((red_skip >> l) & 1u) {
+            } else if constexpr (kGvHalf) {
+                // bf16 accumulation: this lane's 8 channels of the row as one 16-byte bf16x2 vector reduction
+                TV *gp = grad_value + o00;
+                auto red8 = [&](TV *p, float q) {
+                    red_add_v4_bf16x2(p, pack_bf16x2(q * g[0], q * g[1]), pack_bf16x2(q * g[2], q * g[3]),
+                                      pack_bf16x2(q * g[4], q * g[5]), pack_bf16x2(q * g[6], q * g[7]));
+                };
+                if (q00 != 0.f) red8(gp, q00);
+                if (q01 != 0.f) red8(gp + ox, q01);
+                if (q10 != 0.f) red8(gp + oy, q10);
+                if (q11 != 0.f) red8(gp + oy + ox, q11);
             } else if constexpr (!kPaired) {
                 float *gp = grad_value + o00;
                 if (q00 != 0.f) red_add_v4(gp, q00 * gra[0], q00 * gra[1], q00 * gra[2], q00 * gra[3]);
@@ -530,9 +546,25 @@ static int launch_bwd(const char *who, const void *value, const int64_t *hw, con
                       const float *loc, const float *attn, const void *go, float *gv, float *gl,
                       float *ga, const int *row_map, const int *order, int S, int M, int D, int Q,
                       int L, int P, long long rows, cudaStream_t st, unsigned done_levels = 0,
-                      const HostLevels *host_levels = nullptr) {
+                      const HostLevels *host_levels = nullptr, bool gv_bf16 = false) {
     HostLevels hl;
     if (host_levels) hl = *host_levels; else memset(&hl, 0, sizeof(hl));
+    if (gv_bf16) {
+        // grad_value stored and accumulated in bf16: bf16 value rows, head_dim 32, the one-kernel backward only
+        if constexpr (sizeof(T) == 2) {
+            if (D != 32) return fail("%s: bf16 grad_value needs head_dim 32", who);
+            constexpr int G = Vec<T>::N;
+            const int iters = pick_iters(rows, G);
+            const long long per_block = (long long)(kThreads / 32) * G * iters;
+            const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
+            msda_bwd_d32<T, TG, true, bf16><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn, (const TG *)go,
+                                                                     reinterpret_cast<bf16 *>(gv), gl, ga, row_map, S, M, Q,
+                                                                     L, P, (65536 + P - 1) / P, iters, rows, 0u, hl);
+            return check_launch(who);
+        } else {
+            return fail("%s: bf16 grad_value needs a bf16 value tensor", who);
+        }
+    }
     // done_levels: grad_value of these levels is produced elsewhere (dense tensor-core path, msda_dense.cu)
     if (D == 32) {
         constexpr int G = Vec<T>::N;
@@ -607,7 +639,7 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
                               float *grad_value, float *grad_loc, float *grad_attn,
                               const int *row_map, const int *order, int B, int S, int M, int D, int Q,
                               int L, int P, void *stream, unsigned done_levels = 0,
-                              const HostLevels *host_levels = nullptr) {
+                              const HostLevels *host_levels = nullptr, bool gv_bf16 = false) {
     if (int e = check_dims(who, B, S, M, D, Q, L, P)) return e;
     const long long rows = (row_map ? 1ll : (long long)B) * Q * M;
     if (rows == 0) return 0;
@@ -621,9 +653,9 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
     const bool vb = value_dtype == BEVF_DTYPE_BF16, gb = grad_out_dtype == BEVF_DTYPE_BF16;
     if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (grad_out_dtype != BEVF_DTYPE_F32 && !gb))
         return fail("%s: unsupported dtype code", who);
-    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels);
-    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels);
-    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels);
+    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_bf16);
+    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_bf16);
+    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_bf16);
     return fail("%s: fp32 value with bf16 grad_out is not supported", who);
 }
 
@@ -749,6 +781,21 @@ extern "C" int bevf_msda_rows_backward_dense(const void *value, int value_dtype,
                                      R, L, P, stream, handled, &hl);
     if (join) cudaStreamWaitEvent(st, join, 0);
     return e;
+}
+
+extern "C" int bevf_msda_rows_backward_gv(const void *value, int value_dtype, const int64_t *level_hw,
+                                          const int64_t *level_start, const float *loc, const float *attn,
+                                          const void *grad_out, int grad_out_dtype, void *grad_value,
+                                          int grad_value_dtype, float *grad_loc, float *grad_attn,
+                                          const int32_t *row_map, const int32_t *group_order, int B, int S, int M,
+                                          int D, int R, int L, int P, void *stream) {
+    const char *who = "bevf_msda_rows_backward_gv";
+    if (!row_map && R > 0) return fail("%s: row_map is null", who);
+    if (grad_value_dtype != BEVF_DTYPE_F32 && grad_value_dtype != BEVF_DTYPE_BF16)
+        return fail("%s: grad_value must be float32 or bfloat16", who);
+    return msda_backward_impl(who, value, value_dtype, level_hw, level_start, loc, attn, grad_out, grad_out_dtype,
+                              reinterpret_cast<float *>(grad_value), grad_loc, grad_attn, row_map, group_order, B, S, M,
+                              D, R, L, P, stream, 0u, nullptr, grad_value_dtype == BEVF_DTYPE_BF16);
 }
 
 extern "C" int bevf_msda_set_backward_mode(int mode) {

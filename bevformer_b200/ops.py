@@ -262,7 +262,7 @@ def _dense_mode_init(lib) -> None:
 
 
 def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
-                       grad_value=None, group_order=None, dense=None):
+                       grad_value=None, group_order=None, dense=None, gv_dtype=torch.float32):
     """``group_order`` (R,) int32: optional permutation of the rows in which runs of 64 entries are
     spatial neighbours on one value map (see bevf_msda_rows_backward_ordered).
     ``dense`` = (level_hw_host, map_range) for row lists grouped by value map: grad_value of the coarse levels
@@ -274,7 +274,9 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     R, _, L, P, _ = loc.shape
     ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
     if grad_value is None:
-        grad_value = torch.zeros(value.shape, device=value.device, dtype=torch.float32)
+        grad_value = torch.zeros(value.shape, device=value.device, dtype=gv_dtype)
+    elif grad_value.dtype != gv_dtype:
+        raise RuntimeError("grad_value buffer and gv_dtype disagree")
     grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
     grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
     lib = _lib.load()
@@ -282,6 +284,15 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
         if group_order is not None and (group_order.dtype != torch.int32 or group_order.numel() != R
                                         or not group_order.is_cuda):
             raise RuntimeError("group_order must be a CUDA int32 tensor with one entry per row")
+        if gv_dtype != torch.float32:
+            # ``gv_dtype`` = torch.bfloat16: grad_value stored AND accumulated in bf16 (bevf_msda_rows_backward_gv)
+            st = lib.bevf_msda_rows_backward_gv(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                                loc.data_ptr(), attn.data_ptr(), grad_output.data_ptr(),
+                                                _DT[grad_output.dtype], grad_value.data_ptr(), _DT[gv_dtype],
+                                                grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
+                                                _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
+            _lib.check(st, lib)
+            return grad_value, grad_loc, grad_attn
         if dense is not None and group_order is None:
             import ctypes
             _dense_mode_init(lib)
@@ -322,7 +333,7 @@ class SamplerRows(Function):
 
     @staticmethod
     def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index, group_order=None,
-                staged=None):
+                staged=None, gv_bf16=False):
         """``staged`` = (level_hw_host, map_range): use the TMA-staged forward (rows grouped by value map)."""
         if value.dtype == torch.float16:      # the reference widens half inputs (…function.py:93)
             value = value.float()
@@ -334,6 +345,8 @@ class SamplerRows(Function):
             out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         ctx.group_order = group_order
+        # grad_value accumulated in bf16 (half the L2 reduction sectors): only where the caller asks for it
+        ctx.gv_bf16 = bool(gv_bf16) and value.dtype == torch.bfloat16 and value.shape[-1] == 32
         ctx.dense = staged if (staged is not None and value.shape[-1] == 32) else None
         ctx.value_early = getattr(value, "_bevf_early", None)     # see plugin/linear.py::shared_input_projections
         ctx.gv_zero = None
@@ -363,12 +376,16 @@ class SamplerRows(Function):
         if ctx.gv_zero is not None:
             gv0, done = ctx.gv_zero
             torch.cuda.current_stream(value.device).wait_event(done)
-        gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
-                                        group_order=ctx.group_order, dense=ctx.dense)
+        if ctx.gv_bf16 and gv0 is None:
+            gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), None,
+                                            group_order=ctx.group_order, gv_dtype=torch.bfloat16)
+        else:
+            gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
+                                            group_order=ctx.group_order, dense=ctx.dense)
         if ctx.value_early is not None and ctx.value_early(gv):
-            # the producer of `value` took the fp32 gradient (conversion + its GEMMs run off the critical path)
-            return None, gl, ga, None, None, None, None, None
-        return gv.to(value.dtype), gl, ga, None, None, None, None, None
+            # the producer of `value` took the gradient (conversion + its GEMMs run off the critical path)
+            return None, gl, ga, None, None, None, None, None, None
+        return gv.to(value.dtype), gl, ga, None, None, None, None, None, None
 
 
 def sca_prep_forward(raw, ref_cam, pair_q, pair_cam, level_hw, B, Nq, M, L, P):

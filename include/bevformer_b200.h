@@ -139,6 +139,24 @@ BEVF_API int bevf_msda_rows_backward_ordered(const void *value, int value_dtype,
                                              int R, int L, int P, void *stream);
 
 /*
+ * bevf_msda_rows_backward_ordered with a choice of the storage / accumulation type of grad_value.
+ *   grad_value_dtype = BEVF_DTYPE_F32   exactly bevf_msda_rows_backward_ordered
+ *   grad_value_dtype = BEVF_DTYPE_BF16  grad_value is a (B, S, M, D) bf16 buffer (zero-filled or holding a running sum)
+ *       and every corner contribution is ONE 16-byte bf16x2 vector reduction per lane: half the L2 reduction sectors
+ *       of the fp32 path, which is what bounds the backward; the sum is rounded to bf16 at every addition, so this
+ *       is meant for maps where a pixel collects few contributions (TemporalSelfAttention: ~16 per (pixel, head) at
+ *       base; measured error in tests/test_msda_gpu.py).  Needs a bf16 value tensor and head_dim 32; the caller
+ *       gets the gradient in the dtype it converts to anyway (multi_scale_deformable_attn_function.py:146-160
+ *       allocates grad_value in value's dtype).
+ */
+BEVF_API int bevf_msda_rows_backward_gv(const void *value, int value_dtype, const int64_t *level_hw,
+                                        const int64_t *level_start, const float *loc, const float *attn,
+                                        const void *grad_out, int grad_out_dtype, void *grad_value,
+                                        int grad_value_dtype, float *grad_loc, float *grad_attn,
+                                        const int32_t *row_map, const int32_t *group_order, int B, int S, int M,
+                                        int D, int R, int L, int P, void *stream);
+
+/*
  * bevf_msda_rows_forward with the coarse pyramid levels staged in shared memory by TMA.
  * For row lists whose rows are grouped by value map (the SCA pair list: camera-major): a CTA takes one
  * (value map, head) and a share of that map's rows, loads every level that fits -- coarsest first, whole

@@ -260,3 +260,43 @@ def test_staged_forward_equals_plain(dtype, bs):
     wrong[-1], wrong[-2] = (25, 15), (50, 29)
     staged2 = ops.msda_rows_forward_staged(vd, ss, lsi, wrong, loc, attn, map_range)
     assert rel_err(staged2.float(), plain.float()) < tol
+
+
+@pytest.mark.parametrize("which", ["tsa_rows", "small"])
+def test_bf16_accumulated_grad_value(which):
+    """bevf_msda_rows_backward_gv with a bf16 grad_value buffer: every contribution is a bf16x2 vector reduction, the
+    running sum is rounded to bf16 at every addition.  On the TSA launch of the headline benchmark (2 x 40 000 rows,
+    4 points, one 200 x 200 level: ~16 contributions per (pixel, head)) the result must hold the bf16 bar against
+    Oracle-S; grad_loc / grad_attn are those of the fp32 path bit for bit (same kernel, same arithmetic)."""
+    from tools.bench_msda import rig_tsa_rows_inputs
+    if which == "tsa_rows":
+        v, ss, lsi, loc, attn, row_map, order = rig_tsa_rows_inputs(DEV)
+    else:
+        v, ss, lsi, loc, attn = syn.make_msda_inputs(3, [(12, 20), (6, 10)], 500, 8, 32, 4, seed=5, device=DEV)
+        loc, attn = loc.flatten(0, 1).contiguous(), attn.flatten(0, 1).contiguous()
+        row_map = torch.arange(3, device=DEV, dtype=torch.int32).repeat_interleave(500).contiguous()
+        order = None
+    vd = v.to(torch.bfloat16)
+    gout = fixed_projection((loc.shape[0], 256)).to(DEV, torch.bfloat16)
+    gv32, gl32, ga32 = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout, group_order=order)
+    gv16, gl16, ga16 = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout, group_order=order,
+                                              gv_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert gv16.dtype == torch.bfloat16
+    assert torch.equal(gl32, gl16) and torch.equal(ga32, ga16)
+    err_vs_fp32 = rel_err(gv16.float().cpu(), gv32.cpu())
+    rounding_only = rel_err(gv32.to(torch.bfloat16).float().cpu(), gv32.cpu())      # what storing in bf16 costs anyway
+    print(which, "bf16-accumulated grad_value vs fp32 accumulation:", err_vs_fp32, "(rounding of the final sum alone:", rounding_only, ")")
+    assert err_vs_fp32 < TOL[torch.bfloat16]
+    if which == "tsa_rows":
+        rm = row_map.cpu().long()
+        vr, gr = vd.float().cpu(), gout.float().cpu()
+        rgv = torch.zeros_like(gv32, device="cpu")
+        for b in range(vr.shape[0]):
+            idx = (rm == b).nonzero().flatten()
+            a, _, _ = msda_oracle.msda_backward(vr[b:b + 1], ss.cpu(), lsi.cpu(), loc.cpu()[idx][None].contiguous(),
+                                                attn.cpu()[idx][None].contiguous(), gr[idx][None].contiguous())
+            rgv[b] = a[0]
+        err = rel_err(gv16.float().cpu(), rgv)
+        print("bf16-accumulated grad_value vs Oracle-S:", err)
+        assert err < TOL[torch.bfloat16]

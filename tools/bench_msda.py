@@ -187,7 +187,10 @@ def main():
                 per_cam = torch.bincount(row_map[row_map >= 0].long(), minlength=B)
                 ends = per_cam.cumsum(0)
                 dense = (list(w.levels), torch.stack([ends - per_cam, ends], 1).to(torch.int32).contiguous())
-            if row_map is not None:
+            if row_map is not None and dt == torch.bfloat16 and os.environ.get("BENCH_GV", "fp32") == "bf16":
+                gv = torch.zeros(v.shape, device=dev, dtype=torch.bfloat16)        # accumulated in bf16
+                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order, gv_dtype=torch.bfloat16)
+            elif row_map is not None:
                 bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order, dense=dense)
             else:
                 bwd = lambda: ops.msda_backward(vd, ss, lsi, loc, attn, g, gv)
@@ -211,7 +214,7 @@ def main():
             C = M * 32
             bf = B * S * C * sz + nrows * M * L * P * 12 + nrows * C * sz
             bb = bf + B * S * C * 4 + nrows * M * L * P * 12
-            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], bwd_mode=os.environ.get("BEVF_MSDA_BWD", "one"), dense=os.environ.get("BENCH_DENSE", "0") if dense is not None else "0",
+            r = dict(shape=name, rows=nrows, dtype=str(dt).split(".")[-1], gv=os.environ.get("BENCH_GV", "fp32"), bwd_mode=os.environ.get("BEVF_MSDA_BWD", "one"), dense=os.environ.get("BENCH_DENSE", "0") if dense is not None else "0",
                      splat_direct=os.environ.get("BEVF_SPLAT_DIRECT", "0"), fwd_ms=round(t_f, 4),
                      bwd_ms=round(t_b, 4), fwd_alg_MB=round(bf / 1e6, 1), bwd_alg_MB=round(bb / 1e6, 1),
                      fwd_GBs=round(bf / t_f / 1e6, 1), bwd_GBs=round(bb / t_b / 1e6, 1),

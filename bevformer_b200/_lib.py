@@ -34,9 +34,15 @@ SIGNATURES = {
                                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p] + [c_int] * 7 + [c_void_p]),
     "bevf_msda_set_backward_mode": (c_int, [c_int]),
-    "bevf_msda_rows_backward_gv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7
-                                   + [c_void_p]),
+    "bevf_abs_max": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "bevf_msda_rows_backward_f16acc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7
+                                       + [c_void_p]),
+    "bevf_gv16_unscale": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "bevf_msda_rows_backward_mixed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                              c_void_p] + [c_int] * 7 + [c_void_p]),
+    "bevf_gv_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "bevf_msda_rows_backward_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
                                       + [c_int] * 7 + [c_void_p]),

@@ -114,6 +114,7 @@ class GradArena:
         ev = torch.cuda.Event()
         ev.record(main)
         self.side_stream.wait_event(ev)
+        self.side_used = True
         with torch.cuda.stream(self.side_stream):
             fn()
         for t in inputs:                                   # the allocator must not recycle them early
@@ -121,8 +122,10 @@ class GradArena:
 
     def _finalize(self) -> None:
         self.active = False
-        if self.side_stream is not None:
+        if self.side_stream is not None and getattr(self, "side_used", False):
+            # (only when this pass put work there: joining a stream that is not part of an ongoing capture is an error)
             torch.cuda.current_stream(self.acc.device).wait_stream(self.side_stream)
+        self.side_used = False
         if not self.defer_conversion:
             self.convert()
         for p in self.params:

@@ -22,6 +22,8 @@
 //     are reduce-scattered over the group so that the lane that produced the sample's scalars also
 //     finishes grad_loc / grad_attn.  grad_value is scattered with 16 B vector reductions
 //     (REDG.E.ADD.F32x4), never scalar atomics.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -123,9 +125,11 @@ msda_fwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
 // ------------------------------------------------------------------------------------------------
 // kScatter = false: the "gather" half only (grad_loc, grad_attn); grad_value then comes from
 // msda_bwd_splat_d32 (msda_splat.cuh), which merges the reductions of neighbouring rows in registers.
-// TV = storage type of grad_value: float (default: fp32 accumulation), or bf16 -- every contribution is then one
-// 16-byte bf16x2 vector reduction per lane (half the L2 reduction sectors, accumulation rounded to bf16 at every
-// add: for maps where a pixel collects few contributions, e.g. TemporalSelfAttention's single fine level).
+// TV = storage type of grad_value: float (default: fp32 accumulation), or __half -- every contribution is then one
+// 16-byte f16x2 vector reduction per lane into a SCALED fp16 buffer (half the L2 reduction sectors; the scale is the
+// power of two that puts max|grad_out| into [8, 16), gv16_scale(*gv_amax)); meant for maps where a pixel collects
+// few contributions, e.g. TemporalSelfAttention's single fine level (bf16 accumulation was measured at 1.4e-2 of
+// max|grad_value| there -- above the 1e-2 bar; fp16 has three more mantissa bits).
 template <typename T, typename TG, bool kScatter, typename TV = float>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
@@ -134,7 +138,13 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
              TV *__restrict__ grad_value, float *__restrict__ grad_loc,
              float *__restrict__ grad_attn, const int *__restrict__ row_map, int S, int M, int Q,
              int L, int P, int magic, int iters, long long rows, unsigned red_skip,
-             const __grid_constant__ HostLevels host_levels) {
+             const __grid_constant__ HostLevels host_levels, const unsigned *__restrict__ gv_amax = nullptr,
+             __half *__restrict__ gv16 = nullptr, unsigned gv16_mask = 0u, int side_start = 0, int S_side = 0) {
+    // Mixed accumulation (gv16 != nullptr, TV = float): the levels of gv16_mask -- the fine ones, pixels
+    // [0, side_start) of every map, where a pixel collects few contributions -- are accumulated in scaled fp16 into
+    // gv16 (B, side_start, M, 32); the other levels are the pixels [side_start, S) and accumulate in fp32 into
+    // grad_value, which then is the SIDE buffer (B, S_side = S - side_start, M, 32).  The split is planned on the
+    // host: a device pyramid that differs from host_levels is a caller bug and traps.
     // red_skip: bit l set = the grad_value contributions of level l are NOT scattered here (hybrid mode: the
     // coarse levels go through msda_bwd_splat_d32, which merges them in registers, on a second stream)
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
@@ -143,8 +153,10 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     __shared__ unsigned s_skip;
     if (threadIdx.x == 0)     // levels masked for the dense path only if that kernel saw the same pyramid
         s_skip = (red_skip && host_levels.h[0] > 0 && !host_levels_match(host_levels, level_hw, level_start, L)) ? 0u : red_skip;
+    if (gv16 != nullptr && threadIdx.x == 32 && !host_levels_match(host_levels, level_hw, level_start, L)) __trap();
     load_level_tab(level_hw, level_start, L, M * 32, tab);
     red_skip = s_skip;
+    const float gv_sc = gv_amax ? gv16_scale(__ldg(gv_amax)) : 1.f;       // scale of the fp16 accumulators
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES, grp = lane / LANES;
@@ -176,7 +188,7 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     // therefore keeps 4 grad_out channels of its own row and 4 of its partner's, and reads the
     // partner's per-sample scalars with one extra shuffle each.
     constexpr bool kGvHalf = sizeof(TV) == 2;
-    static_assert(!kGvHalf || VEC == 8, "bf16 grad_value needs bf16 value rows (8 channels per lane)");
+    static_assert(!kGvHalf || VEC == 8, "fp16 grad_value needs bf16 value rows (8 channels per lane)");
     constexpr bool kPaired = (VEC == 8) && kScatter && !kGvHalf;
     const bool hi = kPaired && (grp & 4);
     const long long vrow = voff - sub * VEC;                       // element offset of the row in its map
@@ -193,6 +205,14 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
         const long long row_a = hi ? row_p : row, row_b = hi ? row : row_p;
         vrow_a = (hi ? vrow_p : vrow) + chan;
         vrow_b = (hi ? vrow : vrow_p) + chan;
+        if (gv16 != nullptr) {
+            // the fp32 levels live in the side buffer: map stride S_side instead of S, pixel index minus side_start
+            // (the fp16 levels: map stride side_start, see the scatter below)
+            const int b_p = __shfl_xor_sync(0xffffffffu, b, 16);
+            const int b_a = hi ? b_p : b, b_b = hi ? b : b_p;
+            vrow_a -= ((long long)b_a * (S - S_side) + side_start) * pix;
+            vrow_b -= ((long long)b_b * (S - S_side) + side_start) * pix;
+        }
         load_vec<TG, 4>(grad_out + row_a * 32 + chan, gra);
         load_vec<TG, 4>(grad_out + row_b * 32 + chan, grb);
     }
@@ -248,11 +268,12 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
             if constexpr (!kScatter) {
             } else if ((red_skip >> l) & 1u) {
             } else if constexpr (kGvHalf) {
-                // bf16 accumulation: this lane's 8 channels of the row as one 16-byte bf16x2 vector reduction
+                // scaled fp16 accumulation: this lane's 8 channels of the row as one 16-byte f16x2 vector reduction
                 TV *gp = grad_value + o00;
                 auto red8 = [&](TV *p, float q) {
-                    red_add_v4_bf16x2(p, pack_bf16x2(q * g[0], q * g[1]), pack_bf16x2(q * g[2], q * g[3]),
-                                      pack_bf16x2(q * g[4], q * g[5]), pack_bf16x2(q * g[6], q * g[7]));
+                    q *= gv_sc;
+                    red_add_v4_f16x2(p, pack_f16x2(q * g[0], q * g[1]), pack_f16x2(q * g[2], q * g[3]),
+                                     pack_f16x2(q * g[4], q * g[5]), pack_f16x2(q * g[6], q * g[7]));
                 };
                 if (q00 != 0.f) red8(gp, q00);
                 if (q01 != 0.f) red8(gp + ox, q01);
@@ -264,6 +285,18 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
                 if (q01 != 0.f) red_add_v4(gp + ox, q01 * gra[0], q01 * gra[1], q01 * gra[2], q01 * gra[3]);
                 if (q10 != 0.f) red_add_v4(gp + oy, q10 * gra[0], q10 * gra[1], q10 * gra[2], q10 * gra[3]);
                 if (q11 != 0.f) red_add_v4(gp + oy + ox, q11 * gra[0], q11 * gra[1], q11 * gra[2], q11 * gra[3]);
+            } else if ((gv16_mask >> l) & 1u) {
+                // mixed mode, a fine level: scaled fp16 accumulation into the fine buffer (map stride side_start)
+                __half *gp = gv16 + (o00 - (long long)b * S_side * pix);
+                auto red8 = [&](__half *p, float q) {
+                    q *= gv_sc;
+                    red_add_v4_f16x2(p, pack_f16x2(q * g[0], q * g[1]), pack_f16x2(q * g[2], q * g[3]),
+                                     pack_f16x2(q * g[4], q * g[5]), pack_f16x2(q * g[6], q * g[7]));
+                };
+                if (q00 != 0.f) red8(gp, q00);
+                if (q01 != 0.f) red8(gp + ox, q01);
+                if (q10 != 0.f) red8(gp + oy, q10);
+                if (q11 != 0.f) red8(gp + oy + ox, q11);
             } else {
                 const int ep = __shfl_xor_sync(0xffffffffu, e, 16);
                 const float p00 = __shfl_xor_sync(0xffffffffu, q00, 16);
@@ -541,31 +574,55 @@ static int launch_splat(const char *who, const float *loc, const float *attn, co
                                   level_mask, st);
 }
 
+struct MixedGv {               // scaled-fp16 / mixed accumulation of grad_value (see msda_bwd_d32)
+    const unsigned *amax = nullptr;          // float bits of max|grad_out| (bevf_abs_max)
+    __half *gv16 = nullptr;                  // mixed mode: the fine levels' buffer
+    unsigned mask = 0;
+    int side_start = 0, S_side = 0;
+};
+
 template <typename T, typename TG>
 static int launch_bwd(const char *who, const void *value, const int64_t *hw, const int64_t *ls,
                       const float *loc, const float *attn, const void *go, float *gv, float *gl,
                       float *ga, const int *row_map, const int *order, int S, int M, int D, int Q,
                       int L, int P, long long rows, cudaStream_t st, unsigned done_levels = 0,
-                      const HostLevels *host_levels = nullptr, bool gv_bf16 = false) {
+                      const HostLevels *host_levels = nullptr, bool gv_f16 = false,
+                      const MixedGv *mixed = nullptr) {
     HostLevels hl;
     if (host_levels) hl = *host_levels; else memset(&hl, 0, sizeof(hl));
-    if (gv_bf16) {
-        // grad_value stored and accumulated in bf16: bf16 value rows, head_dim 32, the one-kernel backward only
+    if (gv_f16) {
+        // grad_value stored and accumulated in scaled fp16: bf16 value rows, head_dim 32, the one-kernel backward only
         if constexpr (sizeof(T) == 2) {
-            if (D != 32) return fail("%s: bf16 grad_value needs head_dim 32", who);
+            if (D != 32) return fail("%s: fp16 grad_value needs head_dim 32", who);
             constexpr int G = Vec<T>::N;
             const int iters = pick_iters(rows, G);
             const long long per_block = (long long)(kThreads / 32) * G * iters;
             const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
-            msda_bwd_d32<T, TG, true, bf16><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn, (const TG *)go,
-                                                                     reinterpret_cast<bf16 *>(gv), gl, ga, row_map, S, M, Q,
-                                                                     L, P, (65536 + P - 1) / P, iters, rows, 0u, hl);
+            msda_bwd_d32<T, TG, true, __half><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn, (const TG *)go,
+                                                                       reinterpret_cast<__half *>(gv), gl, ga, row_map, S, M,
+                                                                       Q, L, P, (65536 + P - 1) / P, iters, rows, 0u, hl,
+                                                                       mixed ? mixed->amax : nullptr);
             return check_launch(who);
         } else {
-            return fail("%s: bf16 grad_value needs a bf16 value tensor", who);
+            return fail("%s: fp16 grad_value needs a bf16 value tensor", who);
         }
     }
-    // done_levels: grad_value of these levels is produced elsewhere (dense tensor-core path, msda_dense.cu)
+    if (mixed && mixed->gv16) {
+        if constexpr (sizeof(T) == 2) {
+            if (D != 32) return fail("%s: mixed accumulation needs head_dim 32", who);
+            constexpr int G = Vec<T>::N;
+            const int iters = pick_iters(rows, G);
+            const long long per_block = (long long)(kThreads / 32) * G * iters;
+            const unsigned grid = (unsigned)((rows + per_block - 1) / per_block);
+            msda_bwd_d32<T, TG, true><<<grid, kThreads, 0, st>>>((const T *)value, hw, ls, loc, attn, (const TG *)go, gv, gl, ga,
+                                                               row_map, S, M, Q, L, P, (65536 + P - 1) / P, iters, rows, 0u,
+                                                               hl, mixed->amax, mixed->gv16, mixed->mask, mixed->side_start,
+                                                               mixed->S_side);
+            return check_launch(who);
+        } else {
+            return fail("%s: mixed accumulation needs a bf16 value tensor", who);
+        }
+    }
     if (D == 32) {
         constexpr int G = Vec<T>::N;
         const int iters = pick_iters(rows, G);
@@ -639,7 +696,8 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
                               float *grad_value, float *grad_loc, float *grad_attn,
                               const int *row_map, const int *order, int B, int S, int M, int D, int Q,
                               int L, int P, void *stream, unsigned done_levels = 0,
-                              const HostLevels *host_levels = nullptr, bool gv_bf16 = false) {
+                              const HostLevels *host_levels = nullptr, bool gv_f16 = false,
+                              const MixedGv *mixed = nullptr) {
     if (int e = check_dims(who, B, S, M, D, Q, L, P)) return e;
     const long long rows = (row_map ? 1ll : (long long)B) * Q * M;
     if (rows == 0) return 0;
@@ -653,9 +711,9 @@ static int msda_backward_impl(const char *who, const void *value, int value_dtyp
     const bool vb = value_dtype == BEVF_DTYPE_BF16, gb = grad_out_dtype == BEVF_DTYPE_BF16;
     if ((value_dtype != BEVF_DTYPE_F32 && !vb) || (grad_out_dtype != BEVF_DTYPE_F32 && !gb))
         return fail("%s: unsupported dtype code", who);
-    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_bf16);
-    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_bf16);
-    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_bf16);
+    if (!vb && !gb) return launch_bwd<float, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_f16, mixed);
+    if (vb && gb) return launch_bwd<bf16, bf16>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_f16, mixed);
+    if (vb && !gb) return launch_bwd<bf16, float>(who, value, level_hw, level_start, loc, attn, grad_out, grad_value, grad_loc, grad_attn, row_map, order, S, M, D, Q, L, P, rows, st, done_levels, host_levels, gv_f16, mixed);
     return fail("%s: fp32 value with bf16 grad_out is not supported", who);
 }
 
@@ -783,19 +841,57 @@ extern "C" int bevf_msda_rows_backward_dense(const void *value, int value_dtype,
     return e;
 }
 
-extern "C" int bevf_msda_rows_backward_gv(const void *value, int value_dtype, const int64_t *level_hw,
-                                          const int64_t *level_start, const float *loc, const float *attn,
-                                          const void *grad_out, int grad_out_dtype, void *grad_value,
-                                          int grad_value_dtype, float *grad_loc, float *grad_attn,
-                                          const int32_t *row_map, const int32_t *group_order, int B, int S, int M,
-                                          int D, int R, int L, int P, void *stream) {
-    const char *who = "bevf_msda_rows_backward_gv";
+extern "C" int bevf_msda_rows_backward_f16acc(const void *value, int value_dtype, const int64_t *level_hw,
+                                              const int64_t *level_start, const float *loc, const float *attn,
+                                              const void *grad_out, int grad_out_dtype, void *grad_value_f16,
+                                              const uint32_t *amax_bits, float *grad_loc, float *grad_attn,
+                                              const int32_t *row_map, const int32_t *group_order, int B, int S,
+                                              int M, int D, int R, int L, int P, void *stream) {
+    const char *who = "bevf_msda_rows_backward_f16acc";
     if (!row_map && R > 0) return fail("%s: row_map is null", who);
-    if (grad_value_dtype != BEVF_DTYPE_F32 && grad_value_dtype != BEVF_DTYPE_BF16)
-        return fail("%s: grad_value must be float32 or bfloat16", who);
+    if (!grad_value_f16 || !amax_bits) return fail("%s: null pointer argument", who);
+    MixedGv mx;
+    mx.amax = amax_bits;
     return msda_backward_impl(who, value, value_dtype, level_hw, level_start, loc, attn, grad_out, grad_out_dtype,
-                              reinterpret_cast<float *>(grad_value), grad_loc, grad_attn, row_map, group_order, B, S, M,
-                              D, R, L, P, stream, 0u, nullptr, grad_value_dtype == BEVF_DTYPE_BF16);
+                              reinterpret_cast<float *>(grad_value_f16), grad_loc, grad_attn, row_map, group_order, B, S,
+                              M, D, R, L, P, stream, 0u, nullptr, true, &mx);
+}
+
+extern "C" int bevf_msda_rows_backward_mixed(const void *value, int value_dtype, const int64_t *level_hw,
+                                             const int64_t *level_start, const int32_t *level_hw_host,
+                                             const float *loc, const float *attn, const void *grad_out,
+                                             int grad_out_dtype, void *grad_value_fine_f16, float *grad_value_side,
+                                             const uint32_t *amax_bits, int num_f16_levels, float *grad_loc,
+                                             float *grad_attn, const int32_t *row_map, const int32_t *group_order,
+                                             int B, int S, int M, int D, int R, int L, int P, void *stream) {
+    const char *who = "bevf_msda_rows_backward_mixed";
+    if (!row_map && R > 0) return fail("%s: row_map is null", who);
+    if (!level_hw_host || !grad_value_fine_f16 || !grad_value_side || !amax_bits)
+        return fail("%s: null pointer argument", who);
+    if (L <= 1 || L > kMaxLevels || num_f16_levels < 1 || num_f16_levels >= L)
+        return fail("%s: num_f16_levels must be in [1, L - 1]", who);
+    if (value_dtype != BEVF_DTYPE_BF16 || D != 32) return fail("%s: needs a bf16 value tensor and head_dim 32", who);
+    if (!aligned16(grad_value_fine_f16) || !aligned16(grad_value_side))
+        return fail("%s: device pointers must be 16-byte aligned", who);
+    HostLevels hl;
+    memset(&hl, 0, sizeof(hl));
+    long long start = 0;
+    for (int l = 0; l < L; ++l) {
+        const int h = level_hw_host[2 * l], w = level_hw_host[2 * l + 1];
+        if (h <= 0 || w <= 0 || h >= 32768 || w >= 32768) return fail("%s: bad host level shape", who);
+        hl.h[l] = h; hl.w[l] = w; hl.start[l] = (int)start;
+        start += (long long)h * w;
+    }
+    if (start != S) return fail("%s: host level shapes do not add up to S (%lld vs %lld)", who, start, S);
+    MixedGv mx;
+    mx.amax = amax_bits;
+    mx.gv16 = reinterpret_cast<__half *>(grad_value_fine_f16);
+    mx.mask = (1u << num_f16_levels) - 1u;
+    mx.side_start = hl.start[num_f16_levels];
+    mx.S_side = S - mx.side_start;
+    return msda_backward_impl(who, value, value_dtype, level_hw, level_start, loc, attn, grad_out, grad_out_dtype,
+                              grad_value_side, grad_loc, grad_attn, row_map, group_order, B, S, M, D, R, L, P, stream, 0u,
+                              &hl, false, &mx);
 }
 
 extern "C" int bevf_msda_set_backward_mode(int mode) {

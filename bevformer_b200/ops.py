@@ -262,7 +262,7 @@ def _dense_mode_init(lib) -> None:
 
 
 def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
-                       grad_value=None, group_order=None, dense=None, gv_dtype=torch.float32):
+                       grad_value=None, group_order=None, dense=None):
     """``group_order`` (R,) int32: optional permutation of the rows in which runs of 64 entries are
     spatial neighbours on one value map (see bevf_msda_rows_backward_ordered).
     ``dense`` = (level_hw_host, map_range) for row lists grouped by value map: grad_value of the coarse levels
@@ -274,9 +274,7 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     R, _, L, P, _ = loc.shape
     ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
     if grad_value is None:
-        grad_value = torch.zeros(value.shape, device=value.device, dtype=gv_dtype)
-    elif grad_value.dtype != gv_dtype:
-        raise RuntimeError("grad_value buffer and gv_dtype disagree")
+        grad_value = torch.zeros(value.shape, device=value.device, dtype=torch.float32)
     grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
     grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
     lib = _lib.load()
@@ -284,15 +282,6 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
         if group_order is not None and (group_order.dtype != torch.int32 or group_order.numel() != R
                                         or not group_order.is_cuda):
             raise RuntimeError("group_order must be a CUDA int32 tensor with one entry per row")
-        if gv_dtype != torch.float32:
-            # ``gv_dtype`` = torch.bfloat16: grad_value stored AND accumulated in bf16 (bevf_msda_rows_backward_gv)
-            st = lib.bevf_msda_rows_backward_gv(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
-                                                loc.data_ptr(), attn.data_ptr(), grad_output.data_ptr(),
-                                                _DT[grad_output.dtype], grad_value.data_ptr(), _DT[gv_dtype],
-                                                grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
-                                                _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
-            _lib.check(st, lib)
-            return grad_value, grad_loc, grad_attn
         if dense is not None and group_order is None:
             import ctypes
             _dense_mode_init(lib)
@@ -319,6 +308,93 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     return grad_value, grad_loc, grad_attn
 
 
+def abs_max_bits(x: torch.Tensor) -> torch.Tensor:
+    """(1,) int32 device word holding the float bits of max|x| (bevf_abs_max): the scale source of the fp16-accumulated
+    sampler backward."""
+    _need_cuda(x, "x")
+    x = x.contiguous()
+    out = torch.empty(1, device=x.device, dtype=torch.int32)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        st = lib.bevf_abs_max(x.data_ptr(), _DT[x.dtype], x.numel(), out.data_ptr(), _stream_ptr(x))
+    _lib.check(st, lib)
+    return out
+
+
+def msda_rows_backward_f16acc(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
+                              group_order=None, raw=False):
+    """Row-list backward with grad_value accumulated in scaled fp16 (bevf_msda_rows_backward_f16acc): half the L2
+    reduction sectors of the fp32 path.  Returns (grad_value as bf16, grad_loc, grad_attn); ``raw`` adds the fp16
+    accumulators and the amax word (tests)."""
+    for t, n in ((value, "value"), (loc, "sampling_loc"), (attn, "attn_weight"), (row_map, "row_map"),
+                 (grad_output, "grad_output")):
+        _need_cuda(t, n)
+    if value.dtype != torch.bfloat16 or value.shape[-1] != 32:
+        raise RuntimeError("fp16-accumulated backward: value must be bfloat16 with head_dim 32")
+    NB, S, M, D = value.shape
+    R, _, L, P, _ = loc.shape
+    ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
+    grad_output = grad_output.contiguous()
+    amax = abs_max_bits(grad_output)
+    gv16 = torch.zeros(value.shape, device=value.device, dtype=torch.float16)
+    grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
+    grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
+    gv = torch.empty(value.shape, device=value.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        with _timed("msda_rows_backward", value.device, (R, L)):
+            st = lib.bevf_msda_rows_backward_f16acc(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                                    loc.data_ptr(), attn.data_ptr(), grad_output.data_ptr(),
+                                                    _DT[grad_output.dtype], gv16.data_ptr(), amax.data_ptr(),
+                                                    grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
+                                                    _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
+        _lib.check(st, lib)
+        st = lib.bevf_gv16_unscale(gv16.data_ptr(), amax.data_ptr(), gv.data_ptr(), gv.numel(), _stream_ptr(value))
+        _lib.check(st, lib)
+    return (gv, grad_loc, grad_attn, gv16, amax) if raw else (gv, grad_loc, grad_attn)
+
+
+def msda_rows_backward_mixed(value, spatial_shapes, level_start_index, level_hw_host, num_f16_levels, loc, attn,
+                             row_map, grad_output, group_order=None):
+    """Row-list backward with MIXED accumulation (bevf_msda_rows_backward_mixed): the first ``num_f16_levels`` levels
+    in scaled fp16, the others in fp32 into a side buffer that only spans their pixels; one merge pass produces the
+    bf16 gradient.  ``level_hw_host``: [(h, w), ...] python ints that MUST equal the device spatial_shapes."""
+    import ctypes
+    for t, n in ((value, "value"), (loc, "sampling_loc"), (attn, "attn_weight"), (row_map, "row_map"),
+                 (grad_output, "grad_output")):
+        _need_cuda(t, n)
+    if value.dtype != torch.bfloat16 or value.shape[-1] != 32:
+        raise RuntimeError("mixed-accumulation backward: value must be bfloat16 with head_dim 32")
+    NB, S, M, D = value.shape
+    R, _, L, P, _ = loc.shape
+    if len(level_hw_host) != L or not (1 <= num_f16_levels < L):
+        raise RuntimeError("mixed-accumulation backward: level_hw_host / num_f16_levels do not fit the pyramid")
+    ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
+    s_fine = sum(int(h) * int(w) for h, w in level_hw_host[:num_f16_levels])
+    grad_output = grad_output.contiguous()
+    amax = abs_max_bits(grad_output)
+    fine = torch.zeros((NB, s_fine, M, D), device=value.device, dtype=torch.float16)
+    side = torch.zeros((NB, S - s_fine, M, D), device=value.device, dtype=torch.float32)
+    grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
+    grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
+    gv = torch.empty(value.shape, device=value.device, dtype=torch.bfloat16)
+    hw = (ctypes.c_int32 * (2 * L))(*[int(v) for hw_ in level_hw_host for v in hw_])
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        with _timed("msda_rows_backward", value.device, (R, L)):
+            st = lib.bevf_msda_rows_backward_mixed(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                                   ctypes.addressof(hw), loc.data_ptr(), attn.data_ptr(),
+                                                   grad_output.data_ptr(), _DT[grad_output.dtype], fine.data_ptr(),
+                                                   side.data_ptr(), amax.data_ptr(), int(num_f16_levels),
+                                                   grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
+                                                   _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
+        _lib.check(st, lib)
+        st = lib.bevf_gv_merge(fine.data_ptr(), side.data_ptr(), amax.data_ptr(), gv.data_ptr(), NB, S, s_fine, M * D,
+                               _stream_ptr(value))
+        _lib.check(st, lib)
+    return gv, grad_loc, grad_attn
+
+
 # Second stream for work that is off the critical path (weight gradients, zero-fills and projections that
 # are needed later): set by BEVFormerEncoder.enable_grad_arena(overlap=True); None = everything in order.
 AUX_STREAM: dict = {}
@@ -333,7 +409,7 @@ class SamplerRows(Function):
 
     @staticmethod
     def forward(ctx, value, loc, attn, row_map, spatial_shapes, level_start_index, group_order=None,
-                staged=None, gv_bf16=False):
+                staged=None, gv_mode=None):
         """``staged`` = (level_hw_host, map_range): use the TMA-staged forward (rows grouped by value map)."""
         if value.dtype == torch.float16:      # the reference widens half inputs (…function.py:93)
             value = value.float()
@@ -345,8 +421,9 @@ class SamplerRows(Function):
             out = msda_rows_forward(value, spatial_shapes, level_start_index, loc, attn, row_map)
         ctx.save_for_backward(value, loc, attn, row_map, spatial_shapes, level_start_index)
         ctx.group_order = group_order
-        # grad_value accumulated in bf16 (half the L2 reduction sectors): only where the caller asks for it
-        ctx.gv_bf16 = bool(gv_bf16) and value.dtype == torch.bfloat16 and value.shape[-1] == 32
+        # grad_value accumulated in scaled fp16 -- "f16": every level, ("mixed", level_hw_host, n): the first n levels
+        # -- (half the L2 reduction sectors of those levels): only where the caller asks for it
+        ctx.gv_mode = gv_mode if (gv_mode is not None and value.dtype == torch.bfloat16 and value.shape[-1] == 32) else None
         ctx.dense = staged if (staged is not None and value.shape[-1] == 32) else None
         ctx.value_early = getattr(value, "_bevf_early", None)     # see plugin/linear.py::shared_input_projections
         ctx.gv_zero = None
@@ -376,9 +453,13 @@ class SamplerRows(Function):
         if ctx.gv_zero is not None:
             gv0, done = ctx.gv_zero
             torch.cuda.current_stream(value.device).wait_event(done)
-        if ctx.gv_bf16 and gv0 is None:
-            gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), None,
-                                            group_order=ctx.group_order, gv_dtype=torch.bfloat16)
+        if ctx.gv_mode is not None and gv0 is None and grad_out.dtype == torch.bfloat16:
+            if ctx.gv_mode == "f16":
+                gv, gl, ga = msda_rows_backward_f16acc(value, ss, ls, loc, attn, row_map, grad_out, ctx.group_order)
+            else:
+                _, hw_host, nfine = ctx.gv_mode
+                gv, gl, ga = msda_rows_backward_mixed(value, ss, ls, hw_host, nfine, loc, attn, row_map, grad_out,
+                                                      ctx.group_order)
         else:
             gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
                                             group_order=ctx.group_order, dense=ctx.dense)

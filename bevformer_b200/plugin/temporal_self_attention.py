@@ -128,11 +128,11 @@ class TemporalSelfAttention(nn.Module):
                 order = None
                 if bev_hw is not None and bev_hw[0] * bev_hw[1] == nq:
                     order = self._group_order(bs, int(bev_hw[0]), int(bev_hw[1]), query.device)
-                # BEVF_TSA_GV=bf16: grad_value of the BEV maps accumulated in bf16 (~16 contributions per (pixel, head)):
-                # half the L2 reduction sectors of the sampler backward, no fp32 buffer / conversion
-                gv16 = os.environ.get("BEVF_TSA_GV", "fp32") == "bf16"
+                # BEVF_TSA_GV=f16: grad_value of the BEV maps accumulated in scaled fp16 (~16 contributions per (pixel,
+                # head)): half the L2 reduction sectors of the sampler backward
+                gv_mode = "f16" if os.environ.get("BEVF_TSA_GV", "fp32") == "f16" else None
                 out = ops.SamplerRows.apply(v, loc, attn, self._frame_map(bs, nq, query.device), ss, lsi,
-                                            order, None, gv16)
+                                            order, None, gv_mode)
                 w2 = torch.cat([self.output_proj.weight, self.output_proj.weight], 1) * 0.5
                 return linear(out.view(bs, nq, 2 * c), w2, self.output_proj.bias)
             loc, attn = tsa_sampling_head(q_cat, w, b, ref, ss.contiguous(), bs, nq, self.num_heads,

@@ -139,22 +139,44 @@ BEVF_API int bevf_msda_rows_backward_ordered(const void *value, int value_dtype,
                                              int R, int L, int P, void *stream);
 
 /*
- * bevf_msda_rows_backward_ordered with a choice of the storage / accumulation type of grad_value.
- *   grad_value_dtype = BEVF_DTYPE_F32   exactly bevf_msda_rows_backward_ordered
- *   grad_value_dtype = BEVF_DTYPE_BF16  grad_value is a (B, S, M, D) bf16 buffer (zero-filled or holding a running sum)
- *       and every corner contribution is ONE 16-byte bf16x2 vector reduction per lane: half the L2 reduction sectors
- *       of the fp32 path, which is what bounds the backward; the sum is rounded to bf16 at every addition, so this
- *       is meant for maps where a pixel collects few contributions (TemporalSelfAttention: ~16 per (pixel, head) at
- *       base; measured error in tests/test_msda_gpu.py).  Needs a bf16 value tensor and head_dim 32; the caller
- *       gets the gradient in the dtype it converts to anyway (multi_scale_deformable_attn_function.py:146-160
- *       allocates grad_value in value's dtype).
+ * grad_value accumulated in SCALED fp16 instead of fp32.  The sampler backward is bound by the L2 reduction-sector
+ * rate; an fp16 running sum needs half the sectors (one 16-byte f16x2 vector reduction per lane and corner).
+ * fp16 needs a scale: bevf_abs_max puts max|grad_out| (as float bits) into one device word, every kernel of the
+ * path derives the same power of two from it (the maximum lands in [8, 16): sums of thousands of contributions stay
+ * below 65504, values down to 2^-17 of the maximum stay normal numbers).  The running sum is rounded to 11 bits at
+ * every addition, so this is for maps / levels where a (pixel, head) collects few contributions; measured errors
+ * in tests/test_msda_gpu.py (bf16 accumulation -- what the reference's fp16 op class does,
+ * multi_scale_deformable_attn_function.py:146-160 -- was measured at 1.4e-2 on the TSA launch, above the bar).
+ *
+ *   bevf_abs_max(x, dtype, n, amax_bits)      *amax_bits = float bits of max|x| (n a multiple of 8 / 4 elements)
+ *   bevf_msda_rows_backward_f16acc            bevf_msda_rows_backward_ordered with grad_value_f16 (B, S, M, D) fp16,
+ *                                             zero-filled or holding a running sum in the same scale
+ *   bevf_gv16_unscale(gv16, amax, out, n)     out (bf16) = gv16 / scale
+ *   bevf_msda_rows_backward_mixed             the first num_f16_levels pyramid levels (pixels [0, S_fine) of every
+ *                                             map) in scaled fp16 into grad_value_fine_f16 (B, S_fine, M, D), the
+ *                                             others in fp32 into grad_value_side (B, S - S_fine, M, D); the split is
+ *                                             planned from level_hw_host (L, 2) int32 HOST -- a device pyramid that
+ *                                             differs is a caller bug and traps
+ *   bevf_gv_merge(fine, side, amax, out, B, S, S_fine, row_elems)   out (B, S, row_elems) bf16 from both
+ * All need a bf16 value tensor and head_dim 32; grad_loc / grad_attn are those of the fp32 path bit for bit.
  */
-BEVF_API int bevf_msda_rows_backward_gv(const void *value, int value_dtype, const int64_t *level_hw,
-                                        const int64_t *level_start, const float *loc, const float *attn,
-                                        const void *grad_out, int grad_out_dtype, void *grad_value,
-                                        int grad_value_dtype, float *grad_loc, float *grad_attn,
-                                        const int32_t *row_map, const int32_t *group_order, int B, int S, int M,
-                                        int D, int R, int L, int P, void *stream);
+BEVF_API int bevf_abs_max(const void *x, int dtype, int64_t n, uint32_t *amax_bits, void *stream);
+BEVF_API int bevf_msda_rows_backward_f16acc(const void *value, int value_dtype, const int64_t *level_hw,
+                                            const int64_t *level_start, const float *loc, const float *attn,
+                                            const void *grad_out, int grad_out_dtype, void *grad_value_f16,
+                                            const uint32_t *amax_bits, float *grad_loc, float *grad_attn,
+                                            const int32_t *row_map, const int32_t *group_order, int B, int S,
+                                            int M, int D, int R, int L, int P, void *stream);
+BEVF_API int bevf_gv16_unscale(const void *gv16, const uint32_t *amax_bits, void *out_bf16, int64_t n, void *stream);
+BEVF_API int bevf_msda_rows_backward_mixed(const void *value, int value_dtype, const int64_t *level_hw,
+                                           const int64_t *level_start, const int32_t *level_hw_host,
+                                           const float *loc, const float *attn, const void *grad_out,
+                                           int grad_out_dtype, void *grad_value_fine_f16, float *grad_value_side,
+                                           const uint32_t *amax_bits, int num_f16_levels, float *grad_loc,
+                                           float *grad_attn, const int32_t *row_map, const int32_t *group_order,
+                                           int B, int S, int M, int D, int R, int L, int P, void *stream);
+BEVF_API int bevf_gv_merge(const void *fine_f16, const float *side_f32, const uint32_t *amax_bits, void *out_bf16,
+                           int B, int S, int S_fine, int row_elems, void *stream);
 
 /*
  * bevf_msda_rows_forward with the coarse pyramid levels staged in shared memory by TMA.

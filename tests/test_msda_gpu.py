@@ -262,41 +262,95 @@ def test_staged_forward_equals_plain(dtype, bs):
     assert rel_err(staged2.float(), plain.float()) < tol
 
 
-@pytest.mark.parametrize("which", ["tsa_rows", "small"])
-def test_bf16_accumulated_grad_value(which):
-    """bevf_msda_rows_backward_gv with a bf16 grad_value buffer: every contribution is a bf16x2 vector reduction, the
-    running sum is rounded to bf16 at every addition.  On the TSA launch of the headline benchmark (2 x 40 000 rows,
-    4 points, one 200 x 200 level: ~16 contributions per (pixel, head)) the result must hold the bf16 bar against
-    Oracle-S; grad_loc / grad_attn are those of the fp32 path bit for bit (same kernel, same arithmetic)."""
-    from tools.bench_msda import rig_tsa_rows_inputs
+def _oracle_grad_value(vd, ss, lsi, loc, attn, row_map, gout):
+    rm = row_map.cpu().long()
+    vr, gr = vd.float().cpu(), gout.float().cpu()
+    rgv = torch.zeros(vd.shape, dtype=torch.float32)
+    for b in range(vr.shape[0]):
+        idx = (rm == b).nonzero().flatten()
+        if idx.numel() == 0:
+            continue
+        a, _, _ = msda_oracle.msda_backward(vr[b:b + 1], ss.cpu(), lsi.cpu(), loc.cpu()[idx][None].contiguous(),
+                                            attn.cpu()[idx][None].contiguous(), gr[idx][None].contiguous())
+        rgv[b] = a[0]
+    return rgv
+
+
+@pytest.mark.parametrize("which", ["tsa_rows", "sca_mixed", "small", "small_mixed", "tiny_grads"])
+def test_fp16_accumulated_grad_value(which):
+    """grad_value accumulated in SCALED fp16 (bevf_msda_rows_backward_f16acc / _mixed + bevf_abs_max /
+    bevf_gv16_unscale / bevf_gv_merge): one f16x2 vector reduction per lane and corner, the running sum rounded to 11
+    bits at every addition, the scale taken from max|grad_out|.  On the launches of the headline benchmark -- TSA: 2 x
+    40 000 rows, one 200 x 200 level, every level in fp16; SCA: 44 511 pairs, level 0 in fp16, levels 1-3 in fp32 -- the
+    bf16 gradient must hold the bf16 bar against Oracle-S; grad_loc / grad_attn are those of the fp32 path bit for
+    bit.  'tiny_grads': gradients of 1e-6 (what the scale is for)."""
+    from tools.bench_msda import rig_sca_inputs, rig_tsa_rows_inputs
+    order, nfine, gscale = None, 0, 1.0
     if which == "tsa_rows":
         v, ss, lsi, loc, attn, row_map, order = rig_tsa_rows_inputs(DEV)
+    elif which == "sca_mixed":
+        v, ss, lsi, loc, attn, row_map = rig_sca_inputs(DEV)
+        nfine = 1
     else:
-        v, ss, lsi, loc, attn = syn.make_msda_inputs(3, [(12, 20), (6, 10)], 500, 8, 32, 4, seed=5, device=DEV)
+        levels = [(12, 20), (6, 10)] if which != "tiny_grads" else [(9, 16)]
+        v, ss, lsi, loc, attn = syn.make_msda_inputs(3, levels, 500, 8, 32, 4, seed=5, device=DEV)
         loc, attn = loc.flatten(0, 1).contiguous(), attn.flatten(0, 1).contiguous()
         row_map = torch.arange(3, device=DEV, dtype=torch.int32).repeat_interleave(500).contiguous()
-        order = None
+        row_map[17:23] = -1                                   # unused rows
+        nfine = 1 if which == "small_mixed" else 0
+        gscale = 1e-6 if which == "tiny_grads" else 1.0
     vd = v.to(torch.bfloat16)
-    gout = fixed_projection((loc.shape[0], 256)).to(DEV, torch.bfloat16)
+    gout = (fixed_projection((loc.shape[0], 256)) * gscale).to(DEV, torch.bfloat16)
     gv32, gl32, ga32 = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout, group_order=order)
-    gv16, gl16, ga16 = ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, gout, group_order=order,
-                                              gv_dtype=torch.bfloat16)
+    if nfine:
+        hw_host = [tuple(int(x) for x in r) for r in ss.tolist()]
+        gv16, gl16, ga16 = ops.msda_rows_backward_mixed(vd, ss, lsi, hw_host, nfine, loc, attn, row_map, gout, order)
+    else:
+        gv16, gl16, ga16 = ops.msda_rows_backward_f16acc(vd, ss, lsi, loc, attn, row_map, gout, order)
     torch.cuda.synchronize()
-    assert gv16.dtype == torch.bfloat16
-    assert torch.equal(gl32, gl16) and torch.equal(ga32, ga16)
-    err_vs_fp32 = rel_err(gv16.float().cpu(), gv32.cpu())
-    rounding_only = rel_err(gv32.to(torch.bfloat16).float().cpu(), gv32.cpu())      # what storing in bf16 costs anyway
-    print(which, "bf16-accumulated grad_value vs fp32 accumulation:", err_vs_fp32, "(rounding of the final sum alone:", rounding_only, ")")
-    assert err_vs_fp32 < TOL[torch.bfloat16]
-    if which == "tsa_rows":
-        rm = row_map.cpu().long()
-        vr, gr = vd.float().cpu(), gout.float().cpu()
-        rgv = torch.zeros_like(gv32, device="cpu")
-        for b in range(vr.shape[0]):
-            idx = (rm == b).nonzero().flatten()
-            a, _, _ = msda_oracle.msda_backward(vr[b:b + 1], ss.cpu(), lsi.cpu(), loc.cpu()[idx][None].contiguous(),
-                                                attn.cpu()[idx][None].contiguous(), gr[idx][None].contiguous())
-            rgv[b] = a[0]
-        err = rel_err(gv16.float().cpu(), rgv)
-        print("bf16-accumulated grad_value vs Oracle-S:", err)
-        assert err < TOL[torch.bfloat16]
+    assert gv16.dtype == torch.bfloat16 and gv16.shape == gv32.shape
+    used = row_map >= 0
+    assert torch.equal(gl32[used], gl16[used]) and torch.equal(ga32[used], ga16[used])
+    scale = max(gv32.abs().max().item(), 1e-30) if which == "tiny_grads" else None     # relative to max|ref| there
+    def err(a, b):
+        return (a.double() - b.double()).abs().max().item() / scale if scale else rel_err(a, b)
+    e_acc = err(gv16.float().cpu(), gv32.cpu())
+    e_round = err(gv32.to(torch.bfloat16).float().cpu(), gv32.cpu())      # what storing the result in bf16 costs anyway
+    lsl = lsi.tolist() + [int(v.shape[1])]
+    per_level = [err(gv16[:, lsl[i]:lsl[i + 1]].float().cpu(), gv32[:, lsl[i]:lsl[i + 1]].cpu()) for i in range(len(lsl) - 1)]
+    print(which, "fp16-accumulated grad_value vs fp32 accumulation:", e_acc, per_level, "(bf16 rounding of the result alone:", e_round, ")")
+    assert e_acc < TOL[torch.bfloat16]
+    if which in ("tsa_rows", "sca_mixed"):
+        rgv = _oracle_grad_value(vd, ss, lsi, loc, attn, row_map, gout)
+        e = rel_err(gv16.float().cpu(), rgv)
+        print(which, "fp16-accumulated grad_value vs Oracle-S:", e)
+        assert e < TOL[torch.bfloat16]
+
+
+def test_gv16_helpers_against_torch():
+    """bevf_abs_max, the scale derived from it, bevf_gv16_unscale and bevf_gv_merge against tensor ops."""
+    from bevformer_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    for dt, amp in ((torch.bfloat16, 37.5), (torch.float32, 3e-7), (torch.bfloat16, 0.0)):
+        x = (torch.randn(4096 * 8, generator=g) * amp).to(DEV, dt)
+        bits = ops.abs_max_bits(x)
+        got = bits.view(torch.float32).item()
+        assert got == x.float().abs().max().item()
+    x = (torch.randn(1000 * 8, generator=g) * 5).to(DEV, torch.bfloat16)
+    bits = ops.abs_max_bits(x)
+    amax = bits.view(torch.float32).item()
+    import math
+    scale = 2.0 ** (3 - math.floor(math.log2(amax)))
+    assert 8.0 <= amax * scale < 16.0
+    acc = (torch.randn(2, 50, 8, 32, generator=g) * 9).to(DEV, torch.float16)
+    out = torch.empty(acc.shape, device=DEV, dtype=torch.bfloat16)
+    _lib.check(lib.bevf_gv16_unscale(acc.data_ptr(), bits.data_ptr(), out.data_ptr(), acc.numel(), 0), lib)
+    torch.cuda.synchronize()
+    assert torch.equal(out, (acc.float() / scale).to(torch.bfloat16))
+    side = torch.randn(2, 30, 8, 32, generator=g).to(DEV)
+    merged = torch.empty(2, 80, 8, 32, device=DEV, dtype=torch.bfloat16)
+    _lib.check(lib.bevf_gv_merge(acc.data_ptr(), side.data_ptr(), bits.data_ptr(), merged.data_ptr(), 2, 80, 50, 256, 0), lib)
+    torch.cuda.synchronize()
+    assert torch.equal(merged[:, :50], (acc.float() / scale).to(torch.bfloat16))
+    assert torch.equal(merged[:, 50:], side.to(torch.bfloat16))

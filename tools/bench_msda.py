@@ -187,9 +187,12 @@ def main():
                 per_cam = torch.bincount(row_map[row_map >= 0].long(), minlength=B)
                 ends = per_cam.cumsum(0)
                 dense = (list(w.levels), torch.stack([ends - per_cam, ends], 1).to(torch.int32).contiguous())
-            if row_map is not None and dt == torch.bfloat16 and os.environ.get("BENCH_GV", "fp32") == "bf16":
-                gv = torch.zeros(v.shape, device=dev, dtype=torch.bfloat16)        # accumulated in bf16
-                bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order, gv_dtype=torch.bfloat16)
+            gvm = os.environ.get("BENCH_GV", "fp32")
+            if row_map is not None and dt == torch.bfloat16 and gvm == "f16":
+                bwd = lambda: ops.msda_rows_backward_f16acc(vd, ss, lsi, loc, attn, row_map, g, order)
+            elif row_map is not None and dt == torch.bfloat16 and gvm.startswith("mixed") and L > 1:
+                nf = int(gvm[5:] or 1)
+                bwd = lambda: ops.msda_rows_backward_mixed(vd, ss, lsi, [tuple(x) for x in ss.tolist()], nf, loc, attn, row_map, g, order)
             elif row_map is not None:
                 bwd = lambda: ops.msda_rows_backward(vd, ss, lsi, loc, attn, row_map, g, gv, order, dense=dense)
             else:

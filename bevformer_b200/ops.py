@@ -308,6 +308,32 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     return grad_value, grad_loc, grad_attn
 
 
+class LazyGradValue:
+    """grad_value of a sampler backward still in accumulator form (scaled fp16 [+ fp32 side buffer]): ``materialize()``
+    runs the one conversion pass (bevf_gv16_unscale / bevf_gv_merge) on the CURRENT stream and returns the bf16
+    gradient.  Lets the consumer (plugin/linear.py's shared projections) do that pass off the critical path, exactly
+    where it converts an fp32 grad_value."""
+
+    def __init__(self, shape, fine, side, amax):
+        self.shape, self.fine, self.side, self.amax = tuple(shape), fine, side, amax
+        self.tensors = tuple(t for t in (fine, side, amax) if t is not None)
+        self.device = fine.device
+
+    def materialize(self) -> torch.Tensor:
+        nb, s, m, d = self.shape
+        gv = torch.empty(self.shape, device=self.device, dtype=torch.bfloat16)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            if self.side is None:
+                st = lib.bevf_gv16_unscale(self.fine.data_ptr(), self.amax.data_ptr(), gv.data_ptr(), gv.numel(),
+                                           _stream_ptr(gv))
+            else:
+                st = lib.bevf_gv_merge(self.fine.data_ptr(), self.side.data_ptr(), self.amax.data_ptr(), gv.data_ptr(),
+                                       nb, s, self.fine.shape[1], m * d, _stream_ptr(gv))
+        _lib.check(st, lib)
+        return gv
+
+
 def abs_max_bits(x: torch.Tensor) -> torch.Tensor:
     """(1,) int32 device word holding the float bits of max|x| (bevf_abs_max): the scale source of the fp16-accumulated
     sampler backward."""
@@ -322,10 +348,10 @@ def abs_max_bits(x: torch.Tensor) -> torch.Tensor:
 
 
 def msda_rows_backward_f16acc(value, spatial_shapes, level_start_index, loc, attn, row_map, grad_output,
-                              group_order=None, raw=False):
+                              group_order=None, lazy=False):
     """Row-list backward with grad_value accumulated in scaled fp16 (bevf_msda_rows_backward_f16acc): half the L2
-    reduction sectors of the fp32 path.  Returns (grad_value as bf16, grad_loc, grad_attn); ``raw`` adds the fp16
-    accumulators and the amax word (tests)."""
+    reduction sectors of the fp32 path.  Returns (grad_value as bf16 -- or, with ``lazy``, a LazyGradValue --,
+    grad_loc, grad_attn)."""
     for t, n in ((value, "value"), (loc, "sampling_loc"), (attn, "attn_weight"), (row_map, "row_map"),
                  (grad_output, "grad_output")):
         _need_cuda(t, n)
@@ -335,27 +361,25 @@ def msda_rows_backward_f16acc(value, spatial_shapes, level_start_index, loc, att
     R, _, L, P, _ = loc.shape
     ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
     grad_output = grad_output.contiguous()
-    amax = abs_max_bits(grad_output)
-    gv16 = torch.zeros(value.shape, device=value.device, dtype=torch.float16)
     grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
     grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
-    gv = torch.empty(value.shape, device=value.device, dtype=torch.bfloat16)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
-        with _timed("msda_rows_backward", value.device, (R, L)):
-            st = lib.bevf_msda_rows_backward_f16acc(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
-                                                    loc.data_ptr(), attn.data_ptr(), grad_output.data_ptr(),
-                                                    _DT[grad_output.dtype], gv16.data_ptr(), amax.data_ptr(),
-                                                    grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
-                                                    _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
+    with torch.cuda.device(value.device), _timed("msda_rows_backward", value.device, (R, L)):
+        # (the scale source and the zero-fill belong to the op: they are inside the bracket bench.py times)
+        amax = abs_max_bits(grad_output)
+        gv16 = torch.zeros(value.shape, device=value.device, dtype=torch.float16)
+        st = lib.bevf_msda_rows_backward_f16acc(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                                loc.data_ptr(), attn.data_ptr(), grad_output.data_ptr(),
+                                                _DT[grad_output.dtype], gv16.data_ptr(), amax.data_ptr(),
+                                                grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
+                                                _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
         _lib.check(st, lib)
-        st = lib.bevf_gv16_unscale(gv16.data_ptr(), amax.data_ptr(), gv.data_ptr(), gv.numel(), _stream_ptr(value))
-        _lib.check(st, lib)
-    return (gv, grad_loc, grad_attn, gv16, amax) if raw else (gv, grad_loc, grad_attn)
+    gv = LazyGradValue(value.shape, gv16, None, amax)
+    return (gv if lazy else gv.materialize()), grad_loc, grad_attn
 
 
 def msda_rows_backward_mixed(value, spatial_shapes, level_start_index, level_hw_host, num_f16_levels, loc, attn,
-                             row_map, grad_output, group_order=None):
+                             row_map, grad_output, group_order=None, lazy=False):
     """Row-list backward with MIXED accumulation (bevf_msda_rows_backward_mixed): the first ``num_f16_levels`` levels
     in scaled fp16, the others in fp32 into a side buffer that only spans their pixels; one merge pass produces the
     bf16 gradient.  ``level_hw_host``: [(h, w), ...] python ints that MUST equal the device spatial_shapes."""
@@ -372,27 +396,23 @@ def msda_rows_backward_mixed(value, spatial_shapes, level_start_index, level_hw_
     ss, ls = _level_tensors(value, spatial_shapes, level_start_index)
     s_fine = sum(int(h) * int(w) for h, w in level_hw_host[:num_f16_levels])
     grad_output = grad_output.contiguous()
-    amax = abs_max_bits(grad_output)
-    fine = torch.zeros((NB, s_fine, M, D), device=value.device, dtype=torch.float16)
-    side = torch.zeros((NB, S - s_fine, M, D), device=value.device, dtype=torch.float32)
     grad_loc = torch.empty(loc.shape, device=value.device, dtype=torch.float32)
     grad_attn = torch.empty(attn.shape, device=value.device, dtype=torch.float32)
-    gv = torch.empty(value.shape, device=value.device, dtype=torch.bfloat16)
     hw = (ctypes.c_int32 * (2 * L))(*[int(v) for hw_ in level_hw_host for v in hw_])
     lib = _lib.load()
-    with torch.cuda.device(value.device):
-        with _timed("msda_rows_backward", value.device, (R, L)):
-            st = lib.bevf_msda_rows_backward_mixed(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
-                                                   ctypes.addressof(hw), loc.data_ptr(), attn.data_ptr(),
-                                                   grad_output.data_ptr(), _DT[grad_output.dtype], fine.data_ptr(),
-                                                   side.data_ptr(), amax.data_ptr(), int(num_f16_levels),
-                                                   grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
-                                                   _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
+    with torch.cuda.device(value.device), _timed("msda_rows_backward", value.device, (R, L)):
+        amax = abs_max_bits(grad_output)
+        fine = torch.zeros((NB, s_fine, M, D), device=value.device, dtype=torch.float16)
+        side = torch.zeros((NB, S - s_fine, M, D), device=value.device, dtype=torch.float32)
+        st = lib.bevf_msda_rows_backward_mixed(value.data_ptr(), _DT[value.dtype], ss.data_ptr(), ls.data_ptr(),
+                                               ctypes.addressof(hw), loc.data_ptr(), attn.data_ptr(),
+                                               grad_output.data_ptr(), _DT[grad_output.dtype], fine.data_ptr(),
+                                               side.data_ptr(), amax.data_ptr(), int(num_f16_levels),
+                                               grad_loc.data_ptr(), grad_attn.data_ptr(), row_map.data_ptr(),
+                                               _ptr(group_order), NB, S, M, D, R, L, P, _stream_ptr(value))
         _lib.check(st, lib)
-        st = lib.bevf_gv_merge(fine.data_ptr(), side.data_ptr(), amax.data_ptr(), gv.data_ptr(), NB, S, s_fine, M * D,
-                               _stream_ptr(value))
-        _lib.check(st, lib)
-    return gv, grad_loc, grad_attn
+    gv = LazyGradValue(value.shape, fine, side, amax)
+    return (gv if lazy else gv.materialize()), grad_loc, grad_attn
 
 
 # Second stream for work that is off the critical path (weight gradients, zero-fills and projections that
@@ -455,14 +475,17 @@ class SamplerRows(Function):
             torch.cuda.current_stream(value.device).wait_event(done)
         if ctx.gv_mode is not None and gv0 is None and grad_out.dtype == torch.bfloat16:
             if ctx.gv_mode == "f16":
-                gv, gl, ga = msda_rows_backward_f16acc(value, ss, ls, loc, attn, row_map, grad_out, ctx.group_order)
+                gv, gl, ga = msda_rows_backward_f16acc(value, ss, ls, loc, attn, row_map, grad_out, ctx.group_order,
+                                                       lazy=True)
             else:
                 _, hw_host, nfine = ctx.gv_mode
                 gv, gl, ga = msda_rows_backward_mixed(value, ss, ls, hw_host, nfine, loc, attn, row_map, grad_out,
-                                                      ctx.group_order)
-        else:
-            gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
-                                            group_order=ctx.group_order, dense=ctx.dense)
+                                                      ctx.group_order, lazy=True)
+            if ctx.value_early is not None and ctx.value_early(gv):
+                return None, gl, ga, None, None, None, None, None, None      # the producer converts it off the critical path
+            return gv.materialize(), gl, ga, None, None, None, None, None, None
+        gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), gv0,
+                                        group_order=ctx.group_order, dense=ctx.dense)
         if ctx.value_early is not None and ctx.value_early(gv):
             # the producer of `value` took the gradient (conversion + its GEMMs run off the critical path)
             return None, gl, ga, None, None, None, None, None, None

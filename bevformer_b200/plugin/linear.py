@@ -199,14 +199,15 @@ class _SharedInputProjections(Function):
 
         def work():
             # (the fp32 -> bf16 conversion of a sampler's grad_value happens here too, off the critical path)
-            dy2 = dy.reshape(-1, n).to(torch.bfloat16).contiguous()
+            dyt = dy.materialize() if isinstance(dy, ops.LazyGradValue) else dy    # fp16 accumulators -> bf16 here
+            dy2 = dyt.reshape(-1, n).to(torch.bfloat16).contiguous()
             if state["need_dx"]:
                 box["dx"] = ops.linear_dgrad_tc(dy2, w)
             dw_acc, db_acc = ar[1][0].view(n, k), (ar[1][1] if len(ar[1]) > 1 else None)
             ops.linear_wgrad_into(dy2, state["x2"], dw_acc, db_acc)
 
         arena.touch(*[p for p in ar[2] if p is not None])
-        arena.run_off_critical_path(work, dy, state["x2"], w)
+        arena.run_off_critical_path(work, *(dy.tensors if isinstance(dy, ops.LazyGradValue) else (dy,)), state["x2"], w)
         state["early"][l] = box
         return True
 

@@ -501,6 +501,9 @@ def run_ours(args):
     if t_bwd and args.config == "base":
         ab = sca_alg_bytes(w, pairs, True)
         kname = "msda_bwd_d32<bf16,bf16> (SCA sampler backward)"
+        if os.environ.get("BEVF_GV_ACC", "f16") == "f16" and not dense_mode:
+            kname = ("SCA sampler backward: bevf_abs_max + zero-fill of the accumulators + msda_bwd_d32<bf16,bf16> with mixed "
+                     "accumulation (levels 0-1 scaled fp16, levels 2-3 fp32); timed as one op")
         if dense_mode:
             kname = ("SCA sampler backward = msda_bwd_dense_tc (grad_value of levels 1-3: coefficient scatter into UMMA slabs + "
                      "tcgen05.mma into TMEM bins" + (", on the library's second stream" if dense_mode == 2 else "") +
@@ -514,7 +517,9 @@ def run_ours(args):
                 "traffic_source": "profiles/r1p_ncu_full_msda_bwd_raw.csv (msda_bwd_d32<bf16,bf16> with every level on the "
                                   "reduction path, SCA real geometry)" + (
                                       "; the dense path moves the same compulsory bytes (value, grad_out, loc/attn read twice: "
-                                      "+137 MB)" if dense_mode else ""),
+                                      "+137 MB)" if dense_mode else "") + (
+                                      "; with the fp16 accumulation of levels 0-1 the read-modify-write traffic of grad_value is "
+                                      "smaller than in that capture" if os.environ.get("BEVF_GV_ACC", "f16") == "f16" and not dense_mode else ""),
                 "dense_backward_mode": dense_mode,
                 "in_view_pairs": pairs,
                 "alg_bytes_per_launch": ab, "avg_launch_ms": t_bwd,
@@ -572,6 +577,12 @@ def run_ours(args):
                    "gradients": ("flat fp32 gradient arena: one memset + one conversion per step (bevformer_b200/arena.py)"
                                  + ("" if args.no_overlap else "; weight-gradient GEMMs on a side stream, joined at the end of the backward pass")
                                  if arena is not None else "one fp32 buffer + conversion per parameter"),
+                   "sampler_grad_value": (
+                       "fp32 accumulation on every level (BEVF_GV_ACC=fp32)" if os.environ.get("BEVF_GV_ACC", "f16") != "f16"
+                       else "scaled-fp16 accumulation (f16x2 vector reductions, scale from max|grad_out|) on the levels with <= "
+                            + os.environ.get("BEVF_GV_MAXCONTRIB", "64") + " contributions per (pixel, head) on average -- TSA's BEV "
+                            "maps, SCA levels 0-1 at base --, fp32 on the coarse levels; 3.0e-3 / 6.1e-3 of max|grad_value| against "
+                            "the fp32 oracle on these launches (bar 1e-2; tests/test_msda_gpu.py)"),
                    "gemm_backend": ("cuBLASLt via torch (library GEMM; BEVF_GEMM=cublas)"
                                     if os.environ.get("BEVF_GEMM", "tc") == "cublas" else
                                     "hand-written tcgen05 kernels (csrc/gemm.cu): forward, dX and split-M dW")},

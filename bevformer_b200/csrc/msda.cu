@@ -143,8 +143,8 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     // Mixed accumulation (gv16 != nullptr, TV = float): the levels of gv16_mask -- the fine ones, pixels
     // [0, side_start) of every map, where a pixel collects few contributions -- are accumulated in scaled fp16 into
     // gv16 (B, side_start, M, 32); the other levels are the pixels [side_start, S) and accumulate in fp32 into
-    // grad_value, which then is the SIDE buffer (B, S_side = S - side_start, M, 32).  The split is planned on the
-    // host: a device pyramid that differs from host_levels is a caller bug and traps.
+    // grad_value, which then is the SIDE buffer (B, S_side = S - side_start, M, 32).  side_start comes from the host's
+    // copy of the pyramid; the level mask is re-derived from the device pyramid (below).
     // red_skip: bit l set = the grad_value contributions of level l are NOT scattered here (hybrid mode: the
     // coarse levels go through msda_bwd_splat_d32, which merges them in registers, on a second stream)
     constexpr int VEC = Vec<T>::N, LANES = 32 / VEC, G = 32 / LANES;
@@ -153,9 +153,22 @@ msda_bwd_d32(const T *__restrict__ value, const int64_t *__restrict__ level_hw,
     __shared__ unsigned s_skip;
     if (threadIdx.x == 0)     // levels masked for the dense path only if that kernel saw the same pyramid
         s_skip = (red_skip && host_levels.h[0] > 0 && !host_levels_match(host_levels, level_hw, level_start, L)) ? 0u : red_skip;
-    if (gv16 != nullptr && threadIdx.x == 32 && !host_levels_match(host_levels, level_hw, level_start, L)) __trap();
+    __shared__ unsigned s_mask16;
+    if (gv16 != nullptr && threadIdx.x == 32) {
+        // which levels lie in the fp16 part is decided from the DEVICE pyramid: a level is fine if it ends at or before
+        // side_start, coarse if it starts at or after it; a level that straddles the split cannot be served by either
+        // buffer (the caller planned with shapes that are not the device's) and traps
+        unsigned mk = 0;
+        for (int l = 0; l < L; ++l) {
+            const long long a = level_start[l], e = a + level_hw[2 * l] * level_hw[2 * l + 1];
+            if (e <= side_start) mk |= 1u << l;
+            else if (a < side_start) __trap();
+        }
+        s_mask16 = mk;
+    }
     load_level_tab(level_hw, level_start, L, M * 32, tab);
     red_skip = s_skip;
+    if (gv16 != nullptr) gv16_mask = s_mask16;
     const float gv_sc = gv_amax ? gv16_scale(__ldg(gv_amax)) : 1.f;       // scale of the fp16 accumulators
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

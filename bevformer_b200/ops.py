@@ -308,6 +308,28 @@ def msda_rows_backward(value, spatial_shapes, level_start_index, loc, attn, row_
     return grad_value, grad_loc, grad_attn
 
 
+def gv_mode_for(rows_per_map: float, num_points: int, level_hw_host):
+    """How SamplerRows' backward accumulates grad_value for a bf16 value tensor (``gv_mode``):
+    levels on which a (pixel, head) collects on average at most BEVF_GV_MAXCONTRIB (default 64) contributions
+    -- rows_per_map * num_points * 4 / (H * W) -- accumulate in scaled fp16 (half the L2 reduction sectors), the
+    others in fp32.  Measured on the base launches against Oracle-S (tests/test_msda_gpu.py): TSA (16 per pixel)
+    3.0e-3, SCA level 0 (10) 5.2e-3, level 1 (41) 6.1e-3, level 2 (164) 9.6e-3, level 3 (630) 1.3e-2 of max|grad| --
+    hence the cut at 64.  BEVF_GV_ACC=fp32 switches it off.  Returns None, "f16" or ("mixed", shapes, n_fine);
+    only a PREFIX of the pyramid can be fp16 (the fine levels come first in every BEVFormer config)."""
+    if os.environ.get("BEVF_GV_ACC", "f16") != "f16" or not level_hw_host:
+        return None
+    cap = float(os.environ.get("BEVF_GV_MAXCONTRIB", "64"))
+    shapes = [(int(h), int(w)) for h, w in level_hw_host]
+    nfine = 0
+    for h, w in shapes:
+        if rows_per_map * num_points * 4.0 / (h * w) > cap:
+            break
+        nfine += 1
+    if nfine == 0:
+        return None
+    return "f16" if nfine == len(shapes) else ("mixed", shapes, nfine)
+
+
 class LazyGradValue:
     """grad_value of a sampler backward still in accumulator form (scaled fp16 [+ fp32 side buffer]): ``materialize()``
     runs the one conversion pass (bevf_gv16_unscale / bevf_gv_merge) on the CURRENT stream and returns the bf16
@@ -473,7 +495,8 @@ class SamplerRows(Function):
         if ctx.gv_zero is not None:
             gv0, done = ctx.gv_zero
             torch.cuda.current_stream(value.device).wait_event(done)
-        if ctx.gv_mode is not None and gv0 is None and grad_out.dtype == torch.bfloat16:
+        dense_on = ctx.dense is not None and _lib.load().bevf_msda_get_dense_backward() != 0   # explicit opt-in wins
+        if ctx.gv_mode is not None and gv0 is None and grad_out.dtype == torch.bfloat16 and not dense_on:
             if ctx.gv_mode == "f16":
                 gv, gl, ga = msda_rows_backward_f16acc(value, ss, ls, loc, attn, row_map, grad_out, ctx.group_order,
                                                        lazy=True)

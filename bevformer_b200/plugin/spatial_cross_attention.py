@@ -237,21 +237,10 @@ class SpatialCrossAttention(nn.Module):
         staged = None
         if level_hw_host is not None and plan.map_range is not None and len(level_hw_host) == l:
             staged = (level_hw_host, plan.map_range)
-        # BEVF_SCA_GV=mixed: grad_value of the FINE pyramid levels (at most BEVF_GV_MAXCONTRIB, default 16, contributions
-        # per (pixel, head) on average) accumulated in scaled fp16, the coarse ones in fp32 (ops.msda_rows_backward_mixed)
+        # grad_value of the fine pyramid levels accumulated in scaled fp16, the coarse ones in fp32 (ops.gv_mode_for)
         gv_mode = None
-        if os.environ.get("BEVF_SCA_GV", "fp32") == "mixed" and level_hw_host is not None and len(level_hw_host) == l:
-            per_map = plan.row_map.numel() / max(1, bs * ncam)
-            cap = float(os.environ.get("BEVF_GV_MAXCONTRIB", "16"))
-            nfine = 0
-            for h_, w_ in level_hw_host:
-                if per_map * p * 4.0 / (int(h_) * int(w_)) > cap:
-                    break
-                nfine += 1
-            if nfine >= l:
-                gv_mode = "f16"
-            elif nfine >= 1:
-                gv_mode = ("mixed", [(int(h_), int(w_)) for h_, w_ in level_hw_host], nfine)
+        if level_hw_host is not None and len(level_hw_host) == l and v.dtype == torch.bfloat16:
+            gv_mode = ops.gv_mode_for(plan.row_map.numel() / max(1, bs * ncam), p, level_hw_host)
         out = ops.SamplerRows.apply(v, loc, attn, plan.row_map, ss, lsi, None, staged, gv_mode)   # (bs*R, C)
         slots = ops.ScaCombine.apply(out, plan.pair_of, plan.pair_q, plan.inv_count, bs, nq)
         return linear(slots, self.output_proj.weight, self.output_proj.bias)

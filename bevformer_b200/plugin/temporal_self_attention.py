@@ -128,9 +128,11 @@ class TemporalSelfAttention(nn.Module):
                 order = None
                 if bev_hw is not None and bev_hw[0] * bev_hw[1] == nq:
                     order = self._group_order(bs, int(bev_hw[0]), int(bev_hw[1]), query.device)
-                # BEVF_TSA_GV=f16: grad_value of the BEV maps accumulated in scaled fp16 (~16 contributions per (pixel,
-                # head)): half the L2 reduction sectors of the sampler backward
-                gv_mode = "f16" if os.environ.get("BEVF_TSA_GV", "fp32") == "f16" else None
+                # grad_value of the BEV maps accumulated in scaled fp16 when a (pixel, head) collects few contributions
+                # (4 * num_points at nv == nq: 16 at base) -- ops.gv_mode_for; single level: its size is nv, no host shapes
+                gv_mode = None
+                if self.num_levels == 1 and v.dtype == torch.bfloat16:
+                    gv_mode = ops.gv_mode_for(float(nq), self.num_points, [(1, int(nv))])
                 out = ops.SamplerRows.apply(v, loc, attn, self._frame_map(bs, nq, query.device), ss, lsi,
                                             order, None, gv_mode)
                 w2 = torch.cat([self.output_proj.weight, self.output_proj.weight], 1) * 0.5

@@ -154,9 +154,10 @@ BEVF_API int bevf_msda_rows_backward_ordered(const void *value, int value_dtype,
  *   bevf_gv16_unscale(gv16, amax, out, n)     out (bf16) = gv16 / scale
  *   bevf_msda_rows_backward_mixed             the first num_f16_levels pyramid levels (pixels [0, S_fine) of every
  *                                             map) in scaled fp16 into grad_value_fine_f16 (B, S_fine, M, D), the
- *                                             others in fp32 into grad_value_side (B, S - S_fine, M, D); the split is
- *                                             planned from level_hw_host (L, 2) int32 HOST -- a device pyramid that
- *                                             differs is a caller bug and traps
+ *                                             others in fp32 into grad_value_side (B, S - S_fine, M, D); S_fine is
+ *                                             taken from level_hw_host (L, 2) int32 HOST, the kernel re-derives which
+ *                                             levels lie before / after it from the DEVICE pyramid (a device level
+ *                                             that straddles S_fine is a caller bug and traps)
  *   bevf_gv_merge(fine, side, amax, out, B, S, S_fine, row_elems)   out (B, S, row_elems) bf16 from both
  * All need a bf16 value tensor and head_dim 32; grad_loc / grad_attn are those of the fp32 path bit for bit.
  */

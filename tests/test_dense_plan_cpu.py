@@ -55,3 +55,24 @@ def test_base_plan_is_what_the_design_says():
     assert [int(b[2]) for b in bins] == [1, 1, 1, 2]
     bins2, mask2 = plan([(116, 200), (58, 100), (29, 50), (15, 25)], max_pix=2048)
     assert mask2 == 0b1100 and len(bins2) == 1
+
+
+def test_gv_mode_policy(monkeypatch):
+    """ops.gv_mode_for: which pyramid levels accumulate grad_value in scaled fp16 (host logic, no GPU)."""
+    from bevformer_b200 import ops
+    monkeypatch.delenv("BEVF_GV_ACC", raising=False)
+    monkeypatch.delenv("BEVF_GV_MAXCONTRIB", raising=False)
+    base = [(116, 200), (58, 100), (29, 50), (15, 25)]
+    # SCA at base: 44 511 pairs over 6 cameras, 8 points -> 10 / 41 / 164 / 630 contributions per pixel
+    mode = ops.gv_mode_for(44511 / 6, 8, base)
+    assert mode[0] == "mixed" and mode[2] == 2 and mode[1] == base
+    # TSA at base: 40 000 rows per BEV map, 4 points, one level of 40 000 pixels -> 16
+    assert ops.gv_mode_for(40000.0, 4, [(1, 40000)]) == "f16"
+    # bevformer_tiny: one 15 x 25 level, thousands of contributions per pixel -> fp32
+    assert ops.gv_mode_for(2500.0, 8, [(15, 25)]) is None
+    # only a prefix may be fp16: a coarse level in front keeps everything in fp32
+    assert ops.gv_mode_for(44511 / 6, 8, [(15, 25), (116, 200)]) is None
+    monkeypatch.setenv("BEVF_GV_MAXCONTRIB", "16")
+    assert ops.gv_mode_for(44511 / 6, 8, base)[2] == 1
+    monkeypatch.setenv("BEVF_GV_ACC", "fp32")
+    assert ops.gv_mode_for(40000.0, 4, [(1, 40000)]) is None

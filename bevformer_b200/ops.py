@@ -502,6 +502,13 @@ class SamplerRows(Function):
                                                        lazy=True)
             else:
                 _, hw_host, nfine = ctx.gv_mode
+                if sum(h * w for h, w in hw_host) != value.shape[1]:
+                    # a stale host copy of the pyramid (it no longer adds up to S): plain fp32 accumulation instead
+                    gv, gl, ga = msda_rows_backward(value, ss, ls, loc, attn, row_map, grad_out.contiguous(), None,
+                                                    group_order=ctx.group_order)
+                    if ctx.value_early is not None and ctx.value_early(gv):
+                        return None, gl, ga, None, None, None, None, None, None
+                    return gv.to(value.dtype), gl, ga, None, None, None, None, None, None
                 gv, gl, ga = msda_rows_backward_mixed(value, ss, ls, hw_host, nfine, loc, attn, row_map, grad_out,
                                                       ctx.group_order, lazy=True)
             if ctx.value_early is not None and ctx.value_early(gv):

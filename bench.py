@@ -501,7 +501,8 @@ def run_ours(args):
     if t_bwd and args.config == "base":
         ab = sca_alg_bytes(w, pairs, True)
         kname = "msda_bwd_d32<bf16,bf16> (SCA sampler backward)"
-        if os.environ.get("BEVF_GV_ACC", "f16") == "f16" and not dense_mode:
+        gv_f16 = os.environ.get("BEVF_GV_ACC", "f16") == "f16" and not dense_mode
+        if gv_f16:
             kname = ("SCA sampler backward: bevf_abs_max + zero-fill of the accumulators + msda_bwd_d32<bf16,bf16> with mixed "
                      "accumulation (levels 0-1 scaled fp16, levels 2-3 fp32); timed as one op")
         if dense_mode:
@@ -513,13 +514,13 @@ def run_ours(args):
                 "frac": ab / t_bwd / 1e6 / peak, "peak_source": peak_src,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
                 # `ncu --set full` capture named in traffic_source (ncu cannot run inside a bench run)
-                "traffic": 396693504 + 245205504,
-                "traffic_source": "profiles/r1p_ncu_full_msda_bwd_raw.csv (msda_bwd_d32<bf16,bf16> with every level on the "
-                                  "reduction path, SCA real geometry)" + (
-                                      "; the dense path moves the same compulsory bytes (value, grad_out, loc/attn read twice: "
-                                      "+137 MB)" if dense_mode else "") + (
-                                      "; with the fp16 accumulation of levels 0-1 the read-modify-write traffic of grad_value is "
-                                      "smaller than in that capture" if os.environ.get("BEVF_GV_ACC", "f16") == "f16" and not dense_mode else ""),
+                "traffic": (329728512 + 179571712) if gv_f16 else (396693504 + 245205504),
+                "traffic_source": (
+                    "profiles/r2C_ncu_full_msda_bwd_mixed_raw.csv (msda_bwd_d32<bf16,bf16> with levels 0-1 accumulated in scaled fp16, "
+                    "SCA real geometry: 119.5 M L2 reduction sectors instead of 163.3 M)" if gv_f16 else
+                    "profiles/r1p_ncu_full_msda_bwd_raw.csv (msda_bwd_d32<bf16,bf16> with every level on the fp32 reduction path, "
+                    "SCA real geometry)" + ("; the dense path moves the same compulsory bytes (value, grad_out, loc/attn read "
+                                           "twice: +137 MB)" if dense_mode else "")),
                 "dense_backward_mode": dense_mode,
                 "in_view_pairs": pairs,
                 "alg_bytes_per_launch": ab, "avg_launch_ms": t_bwd,

@@ -141,7 +141,8 @@ __device__ __forceinline__ float gv16_scale(unsigned amax_bits) {
     const float a = __uint_as_float(amax_bits);
     if (!(a > 0.f) || !(a < 3.0e38f)) return 1.f;
     const int e = (int)((amax_bits >> 23) & 0xffu) - 127;          // floor(log2(a)) for normal a (denormal: -127)
-    return __uint_as_float((unsigned)(127 + 3 - e) << 23);         // 2^(3 - e)
+    const int ex = min(127 + 3 - e, 254);                          // (maxima below 2^-124 saturate at 2^127)
+    return __uint_as_float((unsigned)ex << 23);                    // 2^(3 - e)
 }
 
 }  // namespace bevf
